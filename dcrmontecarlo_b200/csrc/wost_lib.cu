@@ -1,0 +1,894 @@
+// wost_lib.cu — kernels and the C ABI (include/wost.h) of the B200 Walk-on-Stars engine.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// (see dcrmontecarlo_b200/build.py).  -fmad=false is part of the numerical contract, see wost_device.cuh.
+#include "wost_device.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace wost;
+
+// =================================================================================================
+// errors
+// =================================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(WOST_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+// =================================================================================================
+// handles
+// =================================================================================================
+struct wost_scene {
+    int device = 0;
+    int n_dseg = 0, n_nseg = 0;           // segments
+    int n_dvtx = 0, n_nvtx = 0;
+    float4* dseg = nullptr;               // 2 float4 per Dirichlet segment
+    float4* nseg = nullptr;               // 2 float4 per Neumann segment
+    int sm_count = 0;
+    size_t smem_optin = 0;
+};
+
+struct wost_field {
+    int device = 0;
+    DevField d{};
+    wost_term_t* terms = nullptr;
+    float* grid = nullptr;
+};
+
+// =================================================================================================
+// kernels: the walk
+// =================================================================================================
+struct WalkArgs {
+    const float4* dseg; int n_dseg;
+    const float4* nseg; int n_nseg;
+    int stage_smem;                        // segments fit in shared memory
+    DevFields F;
+    const float* pts; long long n_pts; long long n_walks;
+    int max_steps; float eps, rmin;
+    int sp_mode; float sigma_bar, inv_sigma_bar, sqrt_sigma_bar;
+    const float* icdf; int icdf_len;
+    uint32_t key0, key1; long long point_index_base, walk_offset;
+    float* walk_vals;
+    unsigned long long* counter;           // next unassigned flat walk index
+    unsigned long long* steps_total;
+    int chunk;                             // walks a warp reserves per atomic
+    long long n_trace; int trace_cap; float* trace; int* trace_len;
+};
+
+// One thread per walk, persistent warps with walk regeneration: a lane whose walk has terminated is handed the
+// next walk index in the same loop iteration, so all 32 lanes keep stepping until the job runs dry (walk lengths
+// are geometric-tailed; without regeneration a warp idles until its longest walk ends).  Warps reserve `chunk`
+// consecutive walk indices per global atomic and deal them out with ballot/popc.
+//
+// The loop body restates solvers/WoStSolver.py:206-298 of the reference, quirks included.
+template <bool NEU, bool SRC, bool DELTA, bool TRACE>
+__global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
+    extern __shared__ float4 smem[];
+    const float4* dseg = a.dseg; const float4* nseg = a.nseg;
+    if (a.stage_smem) {
+        float4* sd = smem; float4* sn = smem + 2 * a.n_dseg;
+        for (int i = threadIdx.x; i < 2 * a.n_dseg; i += blockDim.x) sd[i] = a.dseg[i];
+        if (NEU) for (int i = threadIdx.x; i < 2 * a.n_nseg; i += blockDim.x) sn[i] = a.nseg[i];
+        __syncthreads();
+        dseg = sd; nseg = sn;
+    }
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned long long total = (unsigned long long)a.n_pts * (unsigned long long)a.n_walks;
+
+    // warp-uniform reservation [next, end)
+    unsigned long long next = 0, end = 0;
+    bool exhausted = false;
+
+    // per-lane walk state
+    bool active = false, retired = false;
+    unsigned long long id = 0; uint32_t pidx = 0, widx = 0;
+    float x = 0.f, y = 0.f, dD = 1.0f, atten = 1.0f, total_v = 0.0f, phi_n = 0.0f;
+    bool onB = false; int steps = 0;
+    unsigned long long steps_acc = 0;
+
+    while (true) {
+        // ---- regeneration ------------------------------------------------------------------------
+        unsigned need = __ballot_sync(FULL, !active && !retired);
+        while (need) {
+            const bool mine = (need >> lane) & 1u;
+            if (next >= end && !exhausted) {                           // reserve the next chunk of walk indices
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)a.chunk);
+                base = __shfl_sync(FULL, base, 0);
+                next = base < total ? base : total;
+                end = base + (unsigned long long)a.chunk < total ? base + (unsigned long long)a.chunk : total;
+                if (next >= end) exhausted = true;
+            }
+            if (next >= end) { if (mine) retired = true; break; }      // job ran dry
+            const unsigned long long avail = end - next;
+            const int rank = __popc(need & lt_mask);
+            if (mine && (unsigned long long)rank < avail) {
+                id = next + (unsigned long long)rank;
+                const unsigned long long p = id / (unsigned long long)a.n_walks, w = id - p * (unsigned long long)a.n_walks;
+                pidx = (uint32_t)(a.point_index_base + (long long)p); widx = (uint32_t)(a.walk_offset + (long long)w);
+                x = __ldg(a.pts + 2 * p); y = __ldg(a.pts + 2 * p + 1);
+                dD = 1.0f;                                             // :190 sentinel (Q6)
+                atten = 1.0f; total_v = 0.0f; onB = false; phi_n = 0.0f; steps = 0;   // :188-195
+                active = true;
+            }
+            const unsigned long long cnt = (unsigned long long)__popc(need);
+            next += cnt < avail ? cnt : avail;
+            need = __ballot_sync(FULL, !active && !retired);
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        if (active) {
+            // ---- loop condition of the reference: tests the PREVIOUS step's dDirichlet (:206, Q5) ------
+            if (steps < a.max_steps && dD > a.eps) {
+                dD = dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);                 // :208
+                uint32_t o[4];
+                philox4x32_10(pidx, widx, (uint32_t)steps, 0u, a.key0, a.key1, o);
+                float theta = (u24(o[0]) * 2.0f) * 3.14159274101257324f;                // :226
+                if (NEU && onB) theta = theta / 2.0f + phi_n;                           // :227-228 (Q2)
+                float dy, dx; sincosf(theta, &dy, &dx);                                 // :230-232
+
+                float dN = CUDART_INF_F, r, qx, qy;
+                if (NEU) {
+                    // intersect_polylines_jit prologue (:149-159): normalise, offset the origin by 1e-6
+                    const float dn = norm2(dx, dy);
+                    const float ex = dx / dn, ey = dy / dn;
+                    const float ox = x + 1e-6f * ex, oy = y + 1e-6f * ey;
+                    const NeumannQuery nq = neumann_pass<true>(nseg, a.n_nseg, x, y, ox, oy, ex, ey);
+                    dN = nq.sil_d;                                                       // :211
+                    const float m = dN < dD ? dN : dD;                                   // :212
+                    r = (m > a.rmin) ? m : a.rmin;
+                    if (nq.best_k < 0 || nq.best_s > r || nq.best_s <= 0.0f) {           // :166-174 miss
+                        qx = x + r * ex; qy = y + r * ey; onB = false;
+                    } else {                                                             // :176-197 hit
+                        qx = ox + nq.best_s * ex; qy = oy + nq.best_s * ey; onB = true;
+                        phi_n = nseg[2 * nq.best_k + 1].z;                               // atan2 of the left normal (Q3)
+                    }
+                } else {
+                    r = (dD > a.rmin) ? dD : a.rmin;                                     // :215
+                    qx = x + r * dx; qy = y + r * dy; onB = false;                       // :238-239
+                }
+                if (TRACE) {
+                    if ((long long)id < a.n_trace && steps < a.trace_cap) {
+                        float4* t = reinterpret_cast<float4*>(a.trace) + (size_t)id * a.trace_cap + steps;
+                        *t = make_float4(x, y, dD, dN);
+                    }
+                }
+
+                float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f;
+                if (DELTA) {
+                    sbgn = interior_probability(r * a.sqrt_sigma_bar);                   // sigma_bar * |G^sb|(r)
+                    gn = sbgn * a.inv_sigma_bar;                                         // screenedGreensNorm2D (utils.py:29-44)
+                }
+                if (SRC || DELTA) {                                                      // :242 (Q10: also without a source)
+                    float rho;
+                    if (DELTA) {                                                         // screened radius: inverse-CDF table (Q9)
+                        const float pos = u24(o[2]) * (float)(a.icdf_len - 1);
+                        int i = min((int)pos, a.icdf_len - 2);
+                        const float fr = pos - (float)i;
+                        const float t0 = __ldg(a.icdf + i), t1 = __ldg(a.icdf + i + 1);
+                        rho = t0 + fr * (t1 - t0);
+                    } else {                                                             // pdf -ln(rho): product of two uniforms (Q8)
+                        rho = fmaxf(u24p(o[2]) * u24p(o[3]), 1e-6f);
+                    }
+                    const float rs = rho * r;                                            // utils.py:117
+                    sx = x + rs * dx; sy = y + rs * dy;                                  // :245
+                    float contrib = 0.0f;
+                    if (norm2(sx - x, sy - y) > norm2(qx - x, qy - y)) {                 // :248-250
+                        sx = qx; sy = qy;
+                    } else if (SRC) {
+                        if (DELTA)                                                       // :252-254
+                            contrib = (field_eval(a.F.f, sx, sy) * gn / sqrtf(alpha_at(a.F, sx, sy) * alpha_at(a.F, x, y))) * atten;
+                        else
+                            contrib = field_eval(a.F.f, sx, sy) * (r * r / 4.0f);        // :256
+                    }
+                    if (SRC) total_v += contrib;                                         // :258
+                }
+                if (DELTA) {                                                             // :271-284
+                    if (u24(o[1]) > sbgn) {
+                        atten = atten * sqrtf(alpha_at(a.F, qx, qy) / alpha_at(a.F, x, y));
+                        x = qx; y = qy;
+                    } else {
+                        const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy);
+                        const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);
+                        atten = (atten * sqrtf(alpha_at(a.F, sx, sy) / alpha_at(a.F, x, y))) * sc;
+                        x = sx; y = sy;
+                    }
+                } else { x = qx; y = qy; }                                               // :287
+                ++steps;                                                                 // :291
+            } else {
+                // ---- terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7) --------
+                float bc = a.F.g.present ? field_eval(a.F.g, x, y) : 0.0f;
+                if (DELTA) bc = bc * atten;
+                a.walk_vals[id] = total_v + bc;
+                if (TRACE) { if ((long long)id < a.n_trace) a.trace_len[id] = min(steps, a.trace_cap); }
+                steps_acc += (unsigned long long)steps;
+                active = false;
+            }
+        }
+    }
+    // total step count: warp reduce, one atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) steps_acc += __shfl_xor_sync(FULL, steps_acc, off);
+    if (lane == 0 && steps_acc) atomicAdd(a.steps_total, steps_acc);
+}
+
+// =================================================================================================
+// kernels: deterministic statistics
+// =================================================================================================
+// One warp per (point, block of WOST_WALK_BLOCK walks): two-pass mean / M2 in fp64, fixed summation order.
+__global__ void __launch_bounds__(256) block_stats_kernel(const float* __restrict__ vals, long long n_pts, long long n_walks,
+                                                          long long nblk, double* __restrict__ stats) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_pts * nblk) return;
+    const long long p = warp / nblk, b = warp - p * nblk;
+    const long long w0 = b * WOST_WALK_BLOCK;
+    const int n = (int)min((long long)WOST_WALK_BLOCK, n_walks - w0);
+    const float* v = vals + p * n_walks + w0;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += (double)v[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const double mean = s / (double)n;
+    double q = 0.0;
+    for (int i = lane; i < n; i += 32) { const double d = (double)v[i] - mean; q += d * d; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    if (lane == 0) { stats[2 * warp] = mean; stats[2 * warp + 1] = q; }
+}
+
+// One thread per point: Chan merge of its blocks in block order.
+__global__ void merge_stats_kernel(const double* __restrict__ stats, long long n_pts, long long n_walks, long long nblk,
+                                   double* __restrict__ out_mean, double* __restrict__ out_m2) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pts) return;
+    double na = 0.0, ma = 0.0, qa = 0.0;
+    for (long long b = 0; b < nblk; ++b) {
+        const double nb = (double)min((long long)WOST_WALK_BLOCK, n_walks - b * WOST_WALK_BLOCK);
+        const double mb = stats[2 * (p * nblk + b)], qb = stats[2 * (p * nblk + b) + 1];
+        const double n = na + nb, delta = mb - ma;
+        ma = ma + delta * (nb / n);
+        qa = qa + qb + (delta * delta) * (na * nb / n);
+        na = n;
+    }
+    if (out_mean) out_mean[p] = ma;
+    if (out_m2) out_m2[p] = qa;
+}
+
+// =================================================================================================
+// kernels: batched primitives (parity entry points) — the same device functions the walk calls
+// =================================================================================================
+__global__ void geom_distance_kernel(const float4* seg, int n, const float* p, long long B, float* out_d, int* out_seg) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int arg; const float d = dirichlet_distance(seg, n, p[2 * i], p[2 * i + 1], &arg);
+    if (out_d) out_d[i] = d;
+    if (out_seg) out_seg[i] = arg;
+}
+
+// Dirichlet-layout table -> the generic (ax, ay, ux, uy) view used by the Neumann-style queries
+struct SegView { const float4* seg; int n; int dirichlet_layout; };
+__device__ __forceinline__ float4 seg_au(const SegView& s, int k) {
+    if (!s.dirichlet_layout) return s.seg[2 * k];
+    const float4 a = s.seg[2 * k], u = s.seg[2 * k + 1];
+    return make_float4(a.x, a.y, u.x, u.y);
+}
+
+__global__ void geom_silhouette_kernel(SegView sv, const float* p, long long B, float* out_d, uint8_t* out_mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float px = p[2 * i], py = p[2 * i + 1];
+    float sil = CUDART_INF_F, prev_c = 0.0f;
+    for (int k = 0; k < sv.n; ++k) {
+        const float4 s0 = seg_au(sv, k);
+        const float vx = px - s0.x, vy = py - s0.y;
+        const float c = s0.z * vy - s0.w * vx;
+        if (k > 0) {
+            const bool is_sil = prev_c * c < 0.0f;
+            if (is_sil) sil = fminf(sil, norm2_sq(vx, vy));
+            if (out_mask) out_mask[i * (long long)(sv.n - 1) + (k - 1)] = is_sil ? 1 : 0;
+        }
+        prev_c = c;
+    }
+    if (out_d) out_d[i] = sqrtf(sil);
+}
+
+__global__ void geom_ray_kernel(SegView sv, const float* p, const float* dir, long long B, float* out_s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float ox = p[2 * i], oy = p[2 * i + 1], ex = dir[2 * i], ey = dir[2 * i + 1];
+    for (int k = 0; k < sv.n; ++k) {
+        const float4 s0 = seg_au(sv, k);
+        const float wx = ox - s0.x, wy = oy - s0.y;
+        const float d = ex * s0.w - ey * s0.z;
+        const float s = (ex * wy - ey * wx) / d;
+        const float t = (s0.z * wy - s0.w * wx) / d;
+        out_s[i * (long long)sv.n + k] = (s >= 0.0f && s <= 1.0f && t > 0.0f) ? s : CUDART_INF_F;
+    }
+}
+
+__global__ void geom_intersect_kernel(const float4* nseg, int n, const float* p, const float* dir, const float* rr, long long B,
+                                      float* out_pt, float* out_nrm, uint8_t* out_found, int* out_seg) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float x = p[2 * i], y = p[2 * i + 1], dx = dir[2 * i], dy = dir[2 * i + 1], r = rr[i];
+    float qx, qy, nx, ny; int found = 0, segk = -1;
+    const float dn = norm2(dx, dy);
+    if (dn < 1e-10f) { qx = x; qy = y; nx = 1.0f; ny = 0.0f; }                           // :150-154
+    else {
+        const float ex = dx / dn, ey = dy / dn;
+        const float ox = x + 1e-6f * ex, oy = y + 1e-6f * ey;
+        const NeumannQuery nq = neumann_pass<true>(nseg, n, x, y, ox, oy, ex, ey);
+        if (nq.best_k < 0 || nq.best_s > r || nq.best_s <= 0.0f) { qx = x + r * ex; qy = y + r * ey; nx = ny = 0.0f; }
+        else {
+            qx = ox + nq.best_s * ex; qy = oy + nq.best_s * ey;
+            const float4 s1 = nseg[2 * nq.best_k + 1]; nx = s1.x; ny = s1.y; found = 1; segk = nq.best_k;
+        }
+    }
+    if (out_pt) { out_pt[2 * i] = qx; out_pt[2 * i + 1] = qy; }
+    if (out_nrm) { out_nrm[2 * i] = nx; out_nrm[2 * i + 1] = ny; }
+    if (out_found) out_found[i] = (uint8_t)found;
+    if (out_seg) out_seg[i] = segk;
+}
+
+__global__ void field_eval_kernel(DevField F, const float* p, long long B, float* v, float* gx, float* gy, float* lap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float x = p[2 * i], y = p[2 * i + 1];
+    if (v) v[i] = field_eval(F, x, y);
+    if (gx || gy || lap) {
+        const Jet j = field_jet(F, x, y);
+        if (gx) gx[i] = j.gx;
+        if (gy) gy[i] = j.gy;
+        if (lap) lap[i] = j.l;
+    }
+}
+
+__global__ void sigma_prime_kernel(DevFields F, int sp_mode, const float* p, long long B, float* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    out[i] = sigma_prime_at(F, sp_mode, p[2 * i], p[2 * i + 1]);
+}
+
+// FP32 FMA-chain microbenchmark (8 independent chains per thread)
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (float)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 12345.678f) out[0] = s;
+}
+
+// =================================================================================================
+// host helpers
+// =================================================================================================
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// A device view of a caller buffer: used in place if it already lives on the device, otherwise staged through a
+// stream-ordered temporary (copied in for inputs, copied back for outputs on finish()).
+template <typename T>
+struct Staged {
+    T* dev = nullptr; T* host = nullptr; size_t count = 0; bool temp = false; bool is_out = false; cudaStream_t st = nullptr;
+    int init(const T* p, size_t n, bool out, cudaStream_t s) {
+        count = n; is_out = out; st = s;
+        if (!p || n == 0) { dev = nullptr; return 0; }
+        if (is_device_ptr(p)) { dev = const_cast<T*>(p); return 0; }
+        host = const_cast<T*>(p); temp = true;
+        CU(cudaMallocAsync((void**)&dev, n * sizeof(T), s));
+        if (!out) CU(cudaMemcpyAsync(dev, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    int finish() {
+        if (temp && dev) {
+            if (is_out) CU(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+            CU(cudaFreeAsync(dev, st));
+            dev = nullptr;
+        }
+        return 0;
+    }
+    bool host_out() const { return temp && is_out; }
+};
+
+struct DeviceGuard {
+    int prev = -1; bool ok = false;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static std::once_flag g_pool_once[64];
+static void tune_pool(int device) {
+    if (device < 0 || device >= 64) return;
+    std::call_once(g_pool_once[device], [device] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;   // keep freed scratch cached: solves are called in a loop
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    });
+}
+
+static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+typedef void (*walk_kernel_t)(const WalkArgs);
+template <bool TRACE>
+static walk_kernel_t pick_kernel(bool neu, bool src, bool delta) {
+    const int m = (neu ? 4 : 0) | (src ? 2 : 0) | (delta ? 1 : 0);
+    switch (m) {
+        case 0: return walk_kernel<false, false, false, TRACE>;
+        case 1: return walk_kernel<false, false, true, TRACE>;
+        case 2: return walk_kernel<false, true, false, TRACE>;
+        case 3: return walk_kernel<false, true, true, TRACE>;
+        case 4: return walk_kernel<true, false, false, TRACE>;
+        case 5: return walk_kernel<true, false, true, TRACE>;
+        case 6: return walk_kernel<true, true, false, TRACE>;
+        default: return walk_kernel<true, true, true, TRACE>;
+    }
+}
+
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int wost_version(void) { return WOST_VERSION; }
+const char* wost_last_error(void) { return g_err.c_str(); }
+
+int wost_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn, int32_t device, wost_scene_t** out) {
+    if (!out) return fail(WOST_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!dxy || nd < 2) return fail(WOST_ERR_INVALID, "Dirichlet polyline needs at least 2 vertices");
+    if (nn == 1 || nn < 0 || (nn > 0 && !nxy)) return fail(WOST_ERR_INVALID, "Neumann polyline needs 0 or >= 2 vertices");
+    if (is_device_ptr(dxy) || is_device_ptr(nxy)) return fail(WOST_ERR_INVALID, "scene vertices must be host pointers");
+    if (wost_device_count() <= 0) return fail(WOST_ERR_CUDA, "no CUDA device available (libwost has no CPU fallback)");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(WOST_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
+    // volatile: keep the host compiler from contracting these into FMAs — the tables must hold exactly the
+    // fp32 values torch computes for u = b - a and u.u (geometry/PolylinesSimple.py:37,42)
+    std::vector<float4> ds(2 * (size_t)(nd - 1)), ns(nn ? 2 * (size_t)(nn - 1) : 0);
+    for (int k = 0; k + 1 < nd; ++k) {
+        volatile float ax = dxy[2 * k], ay = dxy[2 * k + 1], bx = dxy[2 * k + 2], by = dxy[2 * k + 3];
+        volatile float ux = bx - ax, uy = by - ay;
+        volatile float xx = ux * ux, yy = uy * uy;
+        volatile float uu = xx + yy;
+        if (!(uu > 0.0f) || !std::isfinite(uu))
+            return fail(WOST_ERR_INVALID, "Dirichlet segment " + std::to_string(k) + " has zero or non-finite length");
+        ds[2 * k] = make_float4(ax, ay, bx, by);
+        ds[2 * k + 1] = make_float4(ux, uy, uu, 0.0f);
+    }
+    for (int k = 0; k + 1 < nn; ++k) {
+        volatile float ax = nxy[2 * k], ay = nxy[2 * k + 1], bx = nxy[2 * k + 2], by = nxy[2 * k + 3];
+        volatile float ux = bx - ax, uy = by - ay;
+        volatile float xx = ux * ux;
+        const float len = sqrtf(fmaf(uy, uy, xx));                       // torch.norm (:184)
+        if (!(len > 0.0f) || !std::isfinite(len))
+            return fail(WOST_ERR_INVALID, "Neumann segment " + std::to_string(k) + " has zero or non-finite length");
+        float nx, ny;
+        if (len < 1e-10f) { nx = 0.0f; ny = 1.0f; }                      // :186-189
+        else { volatile float tx = ux / len, ty = uy / len; nx = -ty; ny = tx; }   // :191-194
+        ns[2 * k] = make_float4(ax, ay, ux, uy);
+        ns[2 * k + 1] = make_float4(nx, ny, atan2f(ny, nx), 0.0f);       // solvers/WoStSolver.py:228
+    }
+    auto* s = new wost_scene();
+    s->device = device; s->n_dvtx = nd; s->n_nvtx = nn; s->n_dseg = nd - 1; s->n_nseg = nn ? nn - 1 : 0;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return fail(WOST_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    s->sm_count = prop.multiProcessorCount; s->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaError_t e = cudaMalloc((void**)&s->dseg, ds.size() * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpy(s->dseg, ds.data(), ds.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !ns.empty()) {
+        e = cudaMalloc((void**)&s->nseg, ns.size() * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMemcpy(s->nseg, ns.data(), ns.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(s->dseg); cudaFree(s->nseg); delete s;
+        return fail(WOST_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    }
+    tune_pool(device);
+    *out = s;
+    return WOST_OK;
+}
+
+int wost_scene_destroy(wost_scene_t* s) {
+    if (!s) return WOST_OK;
+    DeviceGuard g(s->device);
+    cudaFree(s->dseg); cudaFree(s->nseg);
+    delete s;
+    return WOST_OK;
+}
+
+int wost_field_create(const wost_field_desc_t* d, int32_t device, wost_field_t** out) {
+    if (!out) return fail(WOST_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!d) return fail(WOST_ERR_INVALID, "desc is NULL");
+    if (d->kind != WOST_FIELD_TERMS && d->kind != WOST_FIELD_GRID) return fail(WOST_ERR_INVALID, "unknown field kind");
+    if (d->kind == WOST_FIELD_TERMS && (d->n_terms < 0 || (d->n_terms > 0 && !d->terms))) return fail(WOST_ERR_INVALID, "bad term list");
+    if (d->kind == WOST_FIELD_GRID && (d->nx < 2 || d->ny < 2 || !d->grid || !(d->dx > 0.0f) || !(d->dy > 0.0f)))
+        return fail(WOST_ERR_INVALID, "grid field needs nx,ny >= 2, positive spacing and data");
+    if (d->mask_kind < WOST_MASK_NONE || d->mask_kind > WOST_MASK_DISC) return fail(WOST_ERR_INVALID, "unknown mask kind");
+    for (int k = 0; d->kind == WOST_FIELD_TERMS && k < d->n_terms; ++k) {
+        const wost_term_t& t = d->terms[k];
+        if (t.kind != WOST_TERM_PRODUCT && t.kind != WOST_TERM_SIGMOID_CIRCLE) return fail(WOST_ERR_INVALID, "unknown term kind");
+        if (t.px < 0 || t.py < 0 || t.px > 16 || t.py > 16) return fail(WOST_ERR_INVALID, "monomial power out of range [0,16]");
+        if (t.t1 < 0 || t.t1 > 2 || t.t2 < 0 || t.t2 > 2) return fail(WOST_ERR_INVALID, "unknown trig kind");
+    }
+    if (wost_device_count() <= 0) return fail(WOST_ERR_CUDA, "no CUDA device available (libwost has no CPU fallback)");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(WOST_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
+    auto* f = new wost_field();
+    f->device = device;
+    DevField& D = f->d;
+    D.present = 1; D.kind = d->kind; D.n_terms = d->kind == WOST_FIELD_TERMS ? d->n_terms : 0; D.mask_kind = d->mask_kind;
+    D.c0 = d->c0; D.m0 = d->mask[0]; D.m1 = d->mask[1]; D.m2 = d->mask[2]; D.m3 = d->mask[3]; D.outside = d->outside;
+    D.nx = d->nx; D.ny = d->ny; D.x0 = d->x0; D.y0 = d->y0; D.dx = d->dx; D.dy = d->dy;
+    cudaError_t e = cudaSuccess;
+    if (D.n_terms > 0) {
+        e = cudaMalloc((void**)&f->terms, sizeof(wost_term_t) * D.n_terms);
+        if (e == cudaSuccess) e = cudaMemcpy(f->terms, d->terms, sizeof(wost_term_t) * D.n_terms, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && d->kind == WOST_FIELD_GRID) {
+        const size_t n = (size_t)d->nx * d->ny;
+        e = cudaMalloc((void**)&f->grid, sizeof(float) * n);
+        if (e == cudaSuccess) e = cudaMemcpy(f->grid, d->grid, sizeof(float) * n, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(f->terms); cudaFree(f->grid); delete f;
+        return fail(WOST_ERR_CUDA, std::string("field upload: ") + cudaGetErrorString(e));
+    }
+    D.terms = f->terms; D.grid = f->grid;
+    *out = f;
+    return WOST_OK;
+}
+
+int wost_field_destroy(wost_field_t* f) {
+    if (!f) return WOST_OK;
+    DeviceGuard g(f->device);
+    cudaFree(f->terms); cudaFree(f->grid);
+    delete f;
+    return WOST_OK;
+}
+
+static DevField dev_field_of(const wost_field_t* f) { DevField z{}; return f ? f->d : z; }
+static DevFields dev_fields_of(const wost_fields_t* F) {
+    DevFields D{};
+    if (F) { D.g = dev_field_of(F->g); D.f = dev_field_of(F->f); D.alpha = dev_field_of(F->alpha); D.sigma = dev_field_of(F->sigma); D.sigma_prime = dev_field_of(F->sigma_prime); }
+    return D;
+}
+
+int wost_field_eval(const wost_field_t* f, const float* p, int64_t B, float* v, float* gx, float* gy, float* lap, void* stream) {
+    if (!f || !p || B < 0) return fail(WOST_ERR_INVALID, "bad arguments");
+    if (B == 0) return WOST_OK;
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Staged<float> sp, sv, sgx, sgy, sl;
+    int rc;
+    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sv.init(v, B, true, st)) || (rc = sgx.init(gx, B, true, st)) ||
+        (rc = sgy.init(gy, B, true, st)) || (rc = sl.init(lap, B, true, st))) return rc;
+    field_eval_kernel<<<blocks_for(B, 256), 256, 0, st>>>(f->d, sp.dev, B, sv.dev, sgx.dev, sgy.dev, sl.dev);
+    CU(cudaGetLastError());
+    const bool sync = sv.host_out() || sgx.host_out() || sgy.host_out() || sl.host_out();
+    if ((rc = sp.finish()) || (rc = sv.finish()) || (rc = sgx.finish()) || (rc = sgy.finish()) || (rc = sl.finish())) return rc;
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+int wost_sigma_prime_eval(const wost_fields_t* F, int32_t sp_mode, const float* p, int64_t B, float* out, void* stream) {
+    if (!F || !p || !out || B < 0) return fail(WOST_ERR_INVALID, "bad arguments");
+    if (sp_mode == WOST_SP_FIELD && !F->sigma_prime) return fail(WOST_ERR_INVALID, "WOST_SP_FIELD needs fields.sigma_prime");
+    const wost_field_t* any = F->alpha ? F->alpha : (F->sigma ? F->sigma : F->sigma_prime);
+    if (!any) return fail(WOST_ERR_INVALID, "no coefficient field given");
+    if (B == 0) return WOST_OK;
+    DeviceGuard g(any->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Staged<float> sp, so; int rc;
+    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = so.init(out, B, true, st))) return rc;
+    sigma_prime_kernel<<<blocks_for(B, 256), 256, 0, st>>>(dev_fields_of(F), sp_mode, sp.dev, B, so.dev);
+    CU(cudaGetLastError());
+    const bool sync = so.host_out();
+    if ((rc = sp.finish()) || (rc = so.finish())) return rc;
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wost_solve_params_t* P,
+               const float* pts_xy, int64_t n_pts,
+               double* out_mean, double* out_m2, double* out_block_stats, float* out_walk_vals, uint64_t* out_steps,
+               int64_t n_trace, int32_t trace_cap, float* out_trace, int32_t* out_trace_len, void* stream) {
+    if (!scene || !P || !pts_xy) return fail(WOST_ERR_INVALID, "scene, params and pts_xy are required");
+    if (n_pts < 0 || P->n_walks <= 0 || P->max_steps < 0) return fail(WOST_ERR_INVALID, "n_pts >= 0, n_walks > 0, max_steps >= 0 required");
+    if (!(P->eps >= 0.0f)) return fail(WOST_ERR_INVALID, "eps must be >= 0");
+    if (n_pts >= (1ll << 32) || P->n_walks + P->walk_offset >= (1ll << 32) || n_pts + P->point_index_base >= (1ll << 32))
+        return fail(WOST_ERR_INVALID, "point and walk indices must fit 32 bits (Philox counter words)");
+    const bool delta = P->delta_tracking != 0;
+    if (delta) {
+        if (!(P->sigma_bar > 0.0f)) return fail(WOST_ERR_INVALID, "delta tracking needs sigma_bar > 0");
+        if (!P->screened_icdf || P->icdf_len < 2) return fail(WOST_ERR_INVALID, "delta tracking needs the screened radius table");
+        if (P->sp_mode < WOST_SP_FULL || P->sp_mode > WOST_SP_FIELD) return fail(WOST_ERR_INVALID, "unknown sp_mode");
+        if (P->sp_mode == WOST_SP_FIELD && !(fields && fields->sigma_prime)) return fail(WOST_ERR_INVALID, "WOST_SP_FIELD needs fields.sigma_prime");
+    }
+    if (n_trace > 0 && (!out_trace || !out_trace_len || trace_cap <= 0)) return fail(WOST_ERR_INVALID, "trace buffers missing");
+    if (fields) {
+        const wost_field_t* fs[5] = {fields->g, fields->f, fields->alpha, fields->sigma, fields->sigma_prime};
+        for (auto* f : fs) if (f && f->device != scene->device) return fail(WOST_ERR_INVALID, "field and scene live on different devices");
+    }
+    if (n_pts == 0) { if (out_steps && !is_device_ptr(out_steps)) *out_steps = 0; return WOST_OK; }
+
+    DeviceGuard g(scene->device);
+    if (!g.ok) return fail(WOST_ERR_CUDA, "cannot select the scene's device");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long W = P->n_walks;
+    const long long nblk = (W + WOST_WALK_BLOCK - 1) / WOST_WALK_BLOCK;
+    const bool trace = n_trace > 0;
+    const bool neu = scene->n_nseg > 0, src = fields && fields->f;
+
+    Staged<float> s_pts, s_vals, s_trace, s_icdf; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
+    int rc;
+    if ((rc = s_pts.init(pts_xy, 2 * n_pts, false, st))) return rc;
+    if ((rc = s_icdf.init(delta ? P->screened_icdf : nullptr, delta ? P->icdf_len : 0, false, st))) return rc;
+    if ((rc = s_mean.init(out_mean, n_pts, true, st)) || (rc = s_m2.init(out_m2, n_pts, true, st)) ||
+        (rc = s_blk.init(out_block_stats, 2 * n_pts * nblk, true, st)) || (rc = s_steps.init(out_steps, 1, true, st)) ||
+        (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * trace_cap * 4 : 0, true, st)) ||
+        (rc = s_tlen.init(out_trace_len, trace ? n_trace : 0, true, st))) return rc;
+
+    // scratch: per-walk totals (unless the caller wants them), counters, block statistics
+    float* vals = nullptr; bool vals_temp = false;
+    if (out_walk_vals && is_device_ptr(out_walk_vals)) vals = out_walk_vals;
+    else { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)n_pts * W, st)); vals_temp = true; }
+    unsigned long long* ctrs = nullptr;
+    CU(cudaMallocAsync((void**)&ctrs, 2 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctrs, 0, 2 * sizeof(unsigned long long), st));
+    double* blk = s_blk.dev; bool blk_temp = false;
+    if (!blk) { CU(cudaMallocAsync((void**)&blk, sizeof(double) * 2 * n_pts * nblk, st)); blk_temp = true; }
+    if (trace) {
+        CU(cudaMemsetAsync(s_trace.dev, 0xff, sizeof(float) * (size_t)n_trace * trace_cap * 4, st));   // NaN fill
+        CU(cudaMemsetAsync(s_tlen.dev, 0, sizeof(int32_t) * n_trace, st));
+    }
+
+    WalkArgs a{};
+    a.dseg = scene->dseg; a.n_dseg = scene->n_dseg; a.nseg = scene->nseg; a.n_nseg = scene->n_nseg;
+    a.F = dev_fields_of(fields);
+    a.pts = s_pts.dev; a.n_pts = n_pts; a.n_walks = W;
+    a.max_steps = P->max_steps; a.eps = P->eps; a.rmin = (float)((double)P->eps / 2.0);   // :167
+    a.sp_mode = P->sp_mode; a.sigma_bar = P->sigma_bar;
+    a.inv_sigma_bar = delta ? (float)(1.0 / (double)P->sigma_bar) : 0.0f;
+    a.sqrt_sigma_bar = delta ? (float)std::sqrt((double)P->sigma_bar) : 0.0f;
+    a.icdf = s_icdf.dev; a.icdf_len = P->icdf_len;
+    a.key0 = (uint32_t)P->seed; a.key1 = (uint32_t)(P->seed >> 32);
+    a.point_index_base = P->point_index_base; a.walk_offset = P->walk_offset;
+    a.walk_vals = vals; a.counter = ctrs; a.steps_total = ctrs + 1;
+    a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
+
+    const int threads = 256;
+    const size_t seg_bytes = sizeof(float4) * 2 * ((size_t)scene->n_dseg + scene->n_nseg);
+    a.stage_smem = seg_bytes <= 96 * 1024 ? 1 : 0;
+    const size_t smem = a.stage_smem ? seg_bytes : 0;
+    walk_kernel_t kern = trace ? pick_kernel<true>(neu, src, delta) : pick_kernel<false>(neu, src, delta);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, threads, smem));
+    if (occ < 1) return fail(WOST_ERR_CUDA, "walk kernel does not fit on an SM");
+    const long long total = (long long)n_pts * W;
+    long long grid = (long long)scene->sm_count * occ;                 // persistent: one wave, a multiple of the SM count
+    const long long want = (total + threads - 1) / threads;
+    if (grid > want) grid = want;
+    const long long nwarps = grid * (threads / 32);
+    long long chunk = total / (nwarps * 8);
+    a.chunk = (int)(chunk < 32 ? 32 : (chunk > 1024 ? 1024 : chunk));
+    if (total < nwarps * 32) a.chunk = (int)((total + nwarps - 1) / nwarps);
+    if (a.chunk < 1) a.chunk = 1;
+
+    kern<<<(unsigned)grid, threads, smem, st>>>(a);
+    CU(cudaGetLastError());
+    block_stats_kernel<<<blocks_for(n_pts * nblk * 32, 256), 256, 0, st>>>(vals, n_pts, W, nblk, blk);
+    CU(cudaGetLastError());
+    if (s_mean.dev || s_m2.dev) {
+        merge_stats_kernel<<<blocks_for(n_pts, 128), 128, 0, st>>>(blk, n_pts, W, nblk, s_mean.dev, s_m2.dev);
+        CU(cudaGetLastError());
+    }
+    if (s_steps.dev) CU(cudaMemcpyAsync(s_steps.dev, ctrs + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    bool sync = s_mean.host_out() || s_m2.host_out() || s_blk.host_out() || s_steps.host_out() || s_trace.host_out() || s_tlen.host_out();
+    if (out_walk_vals && vals_temp) { CU(cudaMemcpyAsync(out_walk_vals, vals, sizeof(float) * (size_t)n_pts * W, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if ((rc = s_pts.finish()) || (rc = s_icdf.finish()) || (rc = s_mean.finish()) || (rc = s_m2.finish()) || (rc = s_blk.finish()) ||
+        (rc = s_steps.finish()) || (rc = s_trace.finish()) || (rc = s_tlen.finish())) return rc;
+    if (vals_temp) CU(cudaFreeAsync(vals, st));
+    if (blk_temp) CU(cudaFreeAsync(blk, st));
+    CU(cudaFreeAsync(ctrs, st));
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+int wost_merge_block_stats(const double* block_stats, int64_t n_pts, int64_t n_walks, int32_t device,
+                           double* out_mean, double* out_m2, void* stream) {
+    if (!block_stats || n_pts < 0 || n_walks <= 0) return fail(WOST_ERR_INVALID, "bad arguments");
+    if (n_pts == 0) return WOST_OK;
+    if (wost_device_count() <= 0) return fail(WOST_ERR_CUDA, "no CUDA device available (libwost has no CPU fallback)");
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nblk = (n_walks + WOST_WALK_BLOCK - 1) / WOST_WALK_BLOCK;
+    Staged<double> sb, sm, sq; int rc;
+    if ((rc = sb.init(block_stats, 2 * n_pts * nblk, false, st)) || (rc = sm.init(out_mean, n_pts, true, st)) || (rc = sq.init(out_m2, n_pts, true, st))) return rc;
+    merge_stats_kernel<<<blocks_for(n_pts, 128), 128, 0, st>>>(sb.dev, n_pts, n_walks, nblk, sm.dev, sq.dev);
+    CU(cudaGetLastError());
+    const bool sync = sm.host_out() || sq.host_out();
+    if ((rc = sb.finish()) || (rc = sm.finish()) || (rc = sq.finish())) return rc;
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+// ---- geometry parity entry points ------------------------------------------------------------------
+static int seg_view(const wost_scene_t* s, int which, SegView* v) {
+    if (!s) return fail(WOST_ERR_INVALID, "scene is NULL");
+    if (which == 0) { v->seg = s->dseg; v->n = s->n_dseg; v->dirichlet_layout = 1; return 0; }
+    if (which == 1) {
+        if (!s->n_nseg) return fail(WOST_ERR_INVALID, "scene has no Neumann polyline");
+        v->seg = s->nseg; v->n = s->n_nseg; v->dirichlet_layout = 0; return 0;
+    }
+    return fail(WOST_ERR_INVALID, "which must be 0 (Dirichlet) or 1 (Neumann)");
+}
+
+int wost_geom_distance(const wost_scene_t* s, int32_t which, const float* p, int64_t B, float* out_d, int32_t* out_seg, void* stream) {
+    SegView v; int rc;
+    if ((rc = seg_view(s, which, &v))) return rc;
+    if (!p || B < 0) return fail(WOST_ERR_INVALID, "bad arguments");
+    if (B == 0) return WOST_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the distance kernel wants the Dirichlet layout; build it on the fly for the Neumann polyline
+    float4* tmp = nullptr;
+    const float4* seg = v.seg;
+    if (!v.dirichlet_layout) {
+        std::vector<float4> h(2 * (size_t)v.n), d(2 * (size_t)v.n);
+        CU(cudaMemcpy(h.data(), v.seg, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < v.n; ++k) {
+            volatile float ax = h[2 * k].x, ay = h[2 * k].y, ux = h[2 * k].z, uy = h[2 * k].w;
+            volatile float xx = ux * ux, yy = uy * uy; volatile float uu = xx + yy;
+            // b is the next segment's a (or a + u for the last one: exact for polylines built from vertices)
+            float bx = (k + 1 < v.n) ? h[2 * k + 2].x : ax + ux, by = (k + 1 < v.n) ? h[2 * k + 2].y : ay + uy;
+            d[2 * k] = make_float4(ax, ay, bx, by); d[2 * k + 1] = make_float4(ux, uy, uu, 0.0f);
+        }
+        CU(cudaMallocAsync((void**)&tmp, sizeof(float4) * d.size(), st));
+        CU(cudaMemcpyAsync(tmp, d.data(), sizeof(float4) * d.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        seg = tmp;
+    }
+    Staged<float> sp, sd; Staged<int32_t> ss;
+    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sd.init(out_d, B, true, st)) || (rc = ss.init(out_seg, B, true, st))) return rc;
+    geom_distance_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, sp.dev, B, sd.dev, ss.dev);
+    CU(cudaGetLastError());
+    const bool sync = sd.host_out() || ss.host_out();
+    if ((rc = sp.finish()) || (rc = sd.finish()) || (rc = ss.finish())) return rc;
+    if (tmp) CU(cudaFreeAsync(tmp, st));
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+int wost_geom_silhouette(const wost_scene_t* s, int32_t which, const float* p, int64_t B, float* out_d, uint8_t* out_mask, void* stream) {
+    SegView v; int rc;
+    if ((rc = seg_view(s, which, &v))) return rc;
+    if (!p || B < 0) return fail(WOST_ERR_INVALID, "bad arguments");
+    if (B == 0) return WOST_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Staged<float> sp, sd; Staged<uint8_t> sm;
+    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sd.init(out_d, B, true, st)) || (rc = sm.init(out_mask, (size_t)B * (v.n - 1), true, st))) return rc;
+    geom_silhouette_kernel<<<blocks_for(B, 256), 256, 0, st>>>(v, sp.dev, B, sd.dev, sm.dev);
+    CU(cudaGetLastError());
+    const bool sync = sd.host_out() || sm.host_out();
+    if ((rc = sp.finish()) || (rc = sd.finish()) || (rc = sm.finish())) return rc;
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+int wost_geom_ray(const wost_scene_t* s, int32_t which, const float* p, const float* dir, int64_t B, float* out_s, void* stream) {
+    SegView v; int rc;
+    if ((rc = seg_view(s, which, &v))) return rc;
+    if (!p || !dir || !out_s || B < 0) return fail(WOST_ERR_INVALID, "bad arguments");
+    if (B == 0) return WOST_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Staged<float> sp, sdir, so;
+    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sdir.init(dir, 2 * B, false, st)) || (rc = so.init(out_s, (size_t)B * v.n, true, st))) return rc;
+    geom_ray_kernel<<<blocks_for(B, 256), 256, 0, st>>>(v, sp.dev, sdir.dev, B, so.dev);
+    CU(cudaGetLastError());
+    const bool sync = so.host_out();
+    if ((rc = sp.finish()) || (rc = sdir.finish()) || (rc = so.finish())) return rc;
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+int wost_geom_intersect(const wost_scene_t* s, int32_t which, const float* p, const float* dir, const float* r, int64_t B,
+                        float* out_pt, float* out_nrm, uint8_t* out_found, int32_t* out_seg, void* stream) {
+    SegView v; int rc;
+    if ((rc = seg_view(s, which, &v))) return rc;
+    if (!p || !dir || !r || B < 0) return fail(WOST_ERR_INVALID, "bad arguments");
+    if (B == 0) return WOST_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // intersect runs on the Neumann layout; convert a Dirichlet polyline on the fly
+    float4* tmp = nullptr; const float4* seg = v.seg;
+    if (v.dirichlet_layout) {
+        std::vector<float4> h(2 * (size_t)v.n), d(2 * (size_t)v.n);
+        CU(cudaMemcpy(h.data(), v.seg, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < v.n; ++k) {
+            const float ax = h[2 * k].x, ay = h[2 * k].y; volatile float ux = h[2 * k + 1].x, uy = h[2 * k + 1].y;
+            volatile float xx = ux * ux;
+            const float len = sqrtf(fmaf(uy, uy, xx));
+            volatile float tx = ux / len, ty = uy / len;
+            d[2 * k] = make_float4(ax, ay, ux, uy); d[2 * k + 1] = make_float4(-ty, tx, atan2f(tx, -ty), 0.0f);
+        }
+        CU(cudaMallocAsync((void**)&tmp, sizeof(float4) * d.size(), st));
+        CU(cudaMemcpyAsync(tmp, d.data(), sizeof(float4) * d.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        seg = tmp;
+    }
+    Staged<float> sp, sdir, sr, spt, snr; Staged<uint8_t> sf; Staged<int32_t> ss;
+    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sdir.init(dir, 2 * B, false, st)) || (rc = sr.init(r, B, false, st)) ||
+        (rc = spt.init(out_pt, 2 * B, true, st)) || (rc = snr.init(out_nrm, 2 * B, true, st)) || (rc = sf.init(out_found, B, true, st)) ||
+        (rc = ss.init(out_seg, B, true, st))) return rc;
+    geom_intersect_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, sp.dev, sdir.dev, sr.dev, B, spt.dev, snr.dev, sf.dev, ss.dev);
+    CU(cudaGetLastError());
+    const bool sync = spt.host_out() || snr.host_out() || sf.host_out() || ss.host_out();
+    if ((rc = sp.finish()) || (rc = sdir.finish()) || (rc = sr.finish()) || (rc = spt.finish()) || (rc = snr.finish()) || (rc = sf.finish()) || (rc = ss.finish())) return rc;
+    if (tmp) CU(cudaFreeAsync(tmp, st));
+    if (sync) CU(cudaStreamSynchronize(st));
+    return WOST_OK;
+}
+
+int wost_fp32_peak(int32_t device, double* out_tflops, double* out_sm_mhz_effective) {
+    if (wost_device_count() <= 0) return fail(WOST_ERR_CUDA, "no CUDA device available");
+    DeviceGuard g(device);
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device));
+    float* d = nullptr;
+    CU(cudaMalloc((void**)&d, sizeof(float)));
+    const int iters = 1 << 15, threads = 256, blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) fma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-7f);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        fma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-7f);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.0f; CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (out_tflops) *out_tflops = best;
+    if (out_sm_mhz_effective) *out_sm_mhz_effective = best * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;
+    return WOST_OK;
+}
+
+}  // extern "C"
