@@ -42,6 +42,16 @@ class Scenario:
     def delta(self) -> bool:
         return self.alpha is not None or self.sigma is not None
 
+    def make_solver(self, **kw):
+        """The product solver (``solvers.WoStSolver.WostSolver_2D``) for this scenario."""
+        from .geometry.PolylinesSimple import PolyLinesSimple
+        from .solvers.WoStSolver import WostSolver_2D
+
+        mode = "ratio" if (self.delta and self.sp_mode == SP_RATIO) else "auto"
+        return WostSolver_2D(PolyLinesSimple(self.dirichlet), self.g,
+                             PolyLinesSimple(self.neumann) if self.neumann is not None else None,
+                             self.f, self.sigma, self.alpha, sigma_prime_mode=mode, **kw)
+
 
 def square(half: float) -> torch.Tensor:
     """Closed CCW square (reference tests/testWoStCorrectness.py:10-20)."""

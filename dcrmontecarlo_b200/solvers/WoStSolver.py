@@ -1,0 +1,312 @@
+"""``WostSolver_2D`` — the reference's solver class (``solvers/WoStSolver.py:15-353``) on a B200.
+
+Same constructor, setters and ``solve`` signature as the reference; the per-point / per-walk / per-step
+Python loop (``_solveUnified``, reference ``:162-316``) is replaced by one persistent CUDA kernel with one
+thread per walk (``csrc/wost_lib.cu``), called through the C ABI in ``include/wost.h``.  Setup that runs once
+per solver (sigma', sigma_bar — reference ``:66-138``) stays on the host in PyTorch.
+
+The callables ``dirichletBoundaryFunction, source, sigma, alpha`` may be :mod:`fields` objects (evaluated
+analytically on the device) or arbitrary Python callables on a ``(2,)`` tensor, which are tabulated on a
+lattice over the domain once and interpolated bilinearly by the kernel.
+
+Extra, keyword-only arguments beyond the reference's: ``seed`` (Philox key; default derived from
+``torch.initial_seed()`` so ``torch.manual_seed(42)`` still makes a script reproducible), ``return_stats``.
+There is no CPU fallback: without the CUDA library or a GPU, ``solve`` raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+try:
+    from ..geometry.Polylines import PolyLines
+    from ..utils import torchGradient, torchLaplacian, gridSampleMinMax
+    from .. import _native as nat
+    from ..fields import Field, GridField, TermField, as_field
+    from .utils import screened_radius_icdf
+except ImportError:  # pragma: no cover - reference-style sys.path layout (solvers.WoStSolver)
+    from geometry.Polylines import PolyLines
+    from utils import torchGradient, torchLaplacian, gridSampleMinMax
+    import _native as nat
+    from fields import Field, GridField, TermField, as_field
+    from solvers.utils import screened_radius_icdf
+
+SP_FULL, SP_RATIO, SP_FIELD = nat.SP_FULL, nat.SP_RATIO, nat.SP_FIELD
+
+_seed_state = {"initial": None, "calls": 0}
+
+
+def _next_seed() -> int:
+    """A fresh Philox key per solve() derived from torch's global seed, so that re-seeding torch replays a script."""
+    init = torch.initial_seed()
+    if _seed_state["initial"] != init:
+        _seed_state["initial"], _seed_state["calls"] = init, 0
+    _seed_state["calls"] += 1
+    return (init * 0x9E3779B97F4A7C15 + _seed_state["calls"] * 0xD1B54A32D192ED03) % (1 << 64)
+
+
+def _zero_boundary(point):
+    return 0.0
+
+
+class WostSolver_2D:
+    """Walk-on-Stars solver for ``-div(alpha grad u) + sigma u = f`` with Dirichlet and zero-Neumann polyline
+    boundaries in 2D (reference class docstring, ``solvers/WoStSolver.py:15-20``)."""
+
+    def __init__(self, dirichletBoundary: PolyLines, dirichletBoundaryFunction: callable = None,
+                 neumannBoundary: PolyLines = None, source: callable = None, sigma: callable = None,
+                 alpha: callable = None, *, field_resolution: int = 257, sigma_prime_resolution: int = 65,
+                 sigma_prime_mode: str = "auto"):
+        """``sigma_prime_mode``: ``"auto"`` differentiates the coefficients like the reference and falls back to
+        ``sigma/alpha`` when that fails; ``"ratio"`` forces the fallback — what the reference ends up with for
+        callables that wrap their result in ``torch.tensor(...)`` (tests/testWostVariableCoefficients.py:49,57,
+        SURVEY Q12) — and ``"full"`` insists on the differentiated form."""
+        if sigma_prime_mode not in ("auto", "ratio", "full"):
+            raise ValueError("sigma_prime_mode must be 'auto', 'ratio' or 'full'")
+        self.sigma_prime_mode = sigma_prime_mode
+        self.dirichletBoundary = dirichletBoundary
+        self.neumannBoundary = neumannBoundary
+        self.field_resolution = int(field_resolution)
+        self.sigma_prime_resolution = int(sigma_prime_resolution)
+
+        # bounding box over both boundaries (reference :38-43)
+        pts = [dirichletBoundary.points] + ([neumannBoundary.points] if neumannBoundary else [])
+        allp = torch.cat([torch.as_tensor(p, dtype=torch.float32).cpu() for p in pts], dim=0)
+        self.domain_bounds = [[allp[:, 0].min(), allp[:, 0].max()], [allp[:, 1].min(), allp[:, 1].max()]]
+
+        self.boundaryDirichlet = _zero_boundary if dirichletBoundaryFunction is None else dirichletBoundaryFunction
+        self.source = source
+        self.use_delta_tracking = False
+        self.sp_mode = SP_FULL
+        self.last_stats = None
+        self._cache: dict = {}
+
+        if sigma is not None or alpha is not None:                      # reference :54-64
+            self.sigma = (lambda point: 0.0) if sigma is None else sigma
+            self.alpha = (lambda point: 1.0) if alpha is None else alpha
+            self._sigma_given, self._alpha_given = sigma is not None, alpha is not None
+            self.sigma_prime, self.sigma_bar = self.buildModifiedSigma()
+            self.use_delta_tracking = True
+
+    # ------------------------------------------------------------------------------------------------
+    # setup (host): sigma' and sigma_bar, reference :66-138
+    # ------------------------------------------------------------------------------------------------
+    def _wrapped(self):
+        def sigma_w(p):
+            v = self.sigma(p)
+            return v if isinstance(v, torch.Tensor) else torch.tensor(v, dtype=torch.float32, requires_grad=True)
+
+        def alpha_w(p):
+            v = self.alpha(p)
+            if not isinstance(v, torch.Tensor):
+                v = torch.tensor(v, dtype=torch.float32, requires_grad=True)
+            return torch.clamp(v, min=1e-8)                              # :84-86
+
+        return sigma_w, alpha_w
+
+    def buildModifiedSigma(self):
+        """Returns ``(sigma_prime, sigma_bar)``: the delta-tracking absorption
+        ``sigma/alpha + (lap(alpha)/alpha - |grad ln alpha|^2 / 2) / 2`` (falling back to ``sigma/alpha`` when the
+        callables cannot be differentiated, as the reference does) and its range over a 50x50 lattice on the
+        bounding box, replaced by 10.0 when not in (0, 1e3] (reference :66-138)."""
+        sigma_w, alpha_w = self._wrapped()
+        self._autograd_failed = False
+
+        def sigma_prime(point):
+            point = point.clone().requires_grad_(True) if not point.requires_grad else point.clone()
+            ratio = sigma_w(point) / alpha_w(point)
+            if self.sigma_prime_mode == "ratio":
+                return ratio
+            try:
+                lap = torchLaplacian(alpha_w, point)
+                g = torchGradient(lambda p: torch.log(alpha_w(p) + 1e-8), point)
+                return ratio + 0.5 * (lap / alpha_w(point) - (g ** 2).sum() / 2.0)
+            except Exception:
+                if self.sigma_prime_mode == "full":
+                    raise
+                self._autograd_failed = True
+                return ratio
+
+        lo, hi = self._sigma_prime_range(sigma_prime)
+        sigma_bar = hi - lo
+        if (sigma_bar <= 0) | (sigma_bar > 1e3):                         # :134-136
+            sigma_bar = 10.0
+        # which device formulation reproduces this closure
+        analytic = all(isinstance(c, TermField) or not given
+                       for c, given in ((self.alpha, self._alpha_given), (self.sigma, self._sigma_given)))
+        if self._autograd_failed or self.sigma_prime_mode == "ratio":
+            self.sp_mode = SP_RATIO
+        elif analytic:
+            self.sp_mode = SP_FULL
+        else:
+            self.sp_mode = SP_FIELD
+        return sigma_prime, sigma_bar
+
+    def _sigma_prime_range(self, sigma_prime):
+        """min / max of sigma' on the 50x50 lattice (reference :130, utils.py:65-120).  Field coefficients are
+        evaluated in one vectorised autograd pass (same elementwise arithmetic), anything else point by point."""
+        fields_only = all(isinstance(c, Field) or not given
+                          for c, given in ((self.alpha, self._alpha_given), (self.sigma, self._sigma_given)))
+        if fields_only:
+            vals = self._sigma_prime_lattice_vectorised(50)
+            if vals is not None:
+                vals = vals[torch.isfinite(vals)]
+                if vals.numel() == 0:
+                    raise ValueError("Function could not be evaluated at any grid points")
+                return vals.min().item(), vals.max().item()
+        lo, hi, _, _ = gridSampleMinMax(sigma_prime, self.domain_bounds, grid_resolution=50)
+        return lo, hi
+
+    def _sigma_prime_lattice_vectorised(self, n):
+        (x0, x1), (y0, y1) = [[float(a), float(b)] for a, b in self.domain_bounds]
+        X, Y = torch.meshgrid(torch.linspace(x0, x1, n), torch.linspace(y0, y1, n), indexing="ij")
+        P = torch.stack([X.flatten(), Y.flatten()], dim=1).requires_grad_(True)
+        ones = torch.ones(P.shape[0])
+        sg = self.sigma(P) if self._sigma_given else torch.zeros(P.shape[0])
+        al = torch.clamp(self.alpha(P), min=1e-8) if self._alpha_given else ones
+        ratio = sg / al
+        if self.sigma_prime_mode == "ratio":
+            return ratio.detach()
+        try:
+            if not self._alpha_given:
+                raise RuntimeError("constant alpha has no graph")         # reference: autograd.grad raises -> ratio
+            (g,) = torch.autograd.grad(al.sum(), P, create_graph=True)
+            lap = torch.zeros(P.shape[0]) + 1e-8
+            try:
+                for i in range(2):
+                    lap = lap + torch.autograd.grad(g[:, i].sum(), P, create_graph=True, retain_graph=True)[0][:, i]
+            except Exception:
+                pass                                                       # utils.py:60-61: keep what was accumulated
+            (lg,) = torch.autograd.grad(torch.log(al + 1e-8).sum(), P, create_graph=True)
+            return (ratio + 0.5 * (lap / al - (lg ** 2).sum(dim=1) / 2.0)).detach()
+        except Exception:
+            if self.sigma_prime_mode == "full":
+                raise
+            self._autograd_failed = True
+            return ratio.detach()
+
+    # ------------------------------------------------------------------------------------------------
+    # setters (reference :141-157)
+    # ------------------------------------------------------------------------------------------------
+    def setBoundaryConditions(self, boundaryDirichlet: callable):
+        self.boundaryDirichlet = boundaryDirichlet
+
+    def setSourceTerm(self, source: callable):
+        self.source = source
+
+    # ------------------------------------------------------------------------------------------------
+    # device objects
+    # ------------------------------------------------------------------------------------------------
+    def _bounds(self):
+        return [[float(a), float(b)] for a, b in self.domain_bounds]
+
+    def _host_field(self, obj, n=None):
+        key = ("host", id(obj), n)
+        if key not in self._cache:
+            self._cache[key] = (obj, as_field(obj, bounds=self._bounds(), n=n or self.field_resolution))
+        return self._cache[key][1]
+
+    def _dev_field(self, obj, device, n=None):
+        if obj is None:
+            return None
+        key = ("dev", id(obj), device, n)
+        if key not in self._cache:
+            self._cache[key] = (obj, nat.DeviceField(self._host_field(obj, n), device))
+        return self._cache[key][1]
+
+    def _scene(self, device):
+        d = nat.host_f32(self.dirichletBoundary.points)
+        n = None if self.neumannBoundary is None else nat.host_f32(self.neumannBoundary.points)
+        key = ("scene", d.tobytes(), None if n is None else n.tobytes(), device)
+        if key not in self._cache:
+            self._cache[key] = nat.Scene(d, n, device)
+        return self._cache[key]
+
+    def _device_problem(self, device):
+        """Scene handle, wost_fields_t and delta-tracking parameters for one device."""
+        g = None if self.boundaryDirichlet is _zero_boundary else self._dev_field(self.boundaryDirichlet, device)
+        f = self._dev_field(self.source, device)
+        alpha = sigma = sp = None
+        icdf = None
+        if self.use_delta_tracking:
+            alpha = self._dev_field(self.alpha, device) if self._alpha_given else None
+            sigma = self._dev_field(self.sigma, device) if self._sigma_given else None
+            if self.sp_mode == SP_FIELD:
+                sp = self._dev_field(self._sigma_prime_plain, device, self.sigma_prime_resolution)
+            key = ("icdf", float(self.sigma_bar), device)
+            if key not in self._cache:
+                self._cache[key] = torch.from_numpy(screened_radius_icdf(self.sigma_bar)).to(torch.device("cuda", device))
+            icdf = self._cache[key]
+        fields = nat.fields_struct(g=g, f=f, alpha=alpha, sigma=sigma, sigma_prime=sp)
+        keep = (g, f, alpha, sigma, sp)
+        return self._scene(device), fields, icdf, keep
+
+    def _sigma_prime_plain(self, point):
+        """sigma' as a plain float callable, for tabulation when the coefficients are not analytic fields."""
+        return float(self.sigma_prime(point))
+
+    # ------------------------------------------------------------------------------------------------
+    # solve (reference :319-353)
+    # ------------------------------------------------------------------------------------------------
+    def solve_raw(self, solvePoints, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None, point_index_base=0,
+                  walk_offset=0, want_block_stats=False, want_walk_vals=False, n_trace=0, trace_cap=0,
+                  device_outputs=False, device=None):
+        """One kernel pass over ``solvePoints`` on one device; returns the raw statistics dict
+        (mean, m2, steps, optional block_stats / walk_vals / trace).  Building block of :meth:`solve`
+        and of the multi-GPU driver (:mod:`dcrmontecarlo_b200.distributed`)."""
+        nat.require_cuda()
+        device = nat.current_device() if device is None else int(device)
+        scene, fields, icdf, keep = self._device_problem(device)
+        if seed is None:
+            seed = _next_seed()
+        res = nat.solve(scene, fields, solvePoints, int(nWalks), int(maxSteps), float(eps),
+                        delta=self.use_delta_tracking, sp_mode=self.sp_mode,
+                        sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
+                        point_index_base=point_index_base, walk_offset=walk_offset, want_block_stats=want_block_stats,
+                        want_walk_vals=want_walk_vals, n_trace=n_trace, trace_cap=trace_cap, device_outputs=device_outputs)
+        res["seed"] = seed
+        return res
+
+    def solve(self, solvePoints: torch.Tensor, nWalks=1000, maxSteps=1000, eps=1e-4, return_history=False, *,
+              seed=None, return_stats=False):
+        """Estimate u at ``solvePoints`` ``(N, 2)`` with ``nWalks`` walks each; returns an ``(N, 1)`` float32 tensor
+        (on the device of ``solvePoints``), or ``(tensor, history_dict)`` with ``return_history=True``."""
+        pts = torch.as_tensor(solvePoints, dtype=torch.float32)
+        P = int(pts.reshape(-1, 2).shape[0])
+        n_trace = trace_cap = 0
+        if return_history:
+            trace_cap = int(min(maxSteps, 4096))
+            n_trace = P * int(nWalks)
+            if n_trace * trace_cap * 16 > (1 << 30):
+                raise ValueError("return_history would need more than 1 GiB of trace; lower nWalks, maxSteps or the point count")
+        res = self.solve_raw(pts, nWalks, maxSteps, eps, seed=seed, want_walk_vals=return_history, n_trace=n_trace, trace_cap=trace_cap)
+        mean = torch.from_numpy(res["mean"])
+        n = float(nWalks)
+        stderr = torch.sqrt(torch.from_numpy(res["m2"]) / max(n - 1.0, 1.0) / n)
+        self.last_stats = dict(mean=mean, stderr=stderr, n_walks=int(nWalks), total_steps=int(res["steps"][0]), seed=res["seed"])
+        out = mean.to(torch.float32).unsqueeze(1).to(pts.device)
+        extras = []
+        if return_history:
+            extras.append(self._history(res, pts.reshape(-1, 2), int(nWalks)))
+        if return_stats:
+            extras.append(self.last_stats)
+        return (out, *extras) if extras else out
+
+    def _history(self, res, pts, W):
+        """History dictionary in the reference's schema (:335-349) rebuilt from the device trace buffer.  Per-step
+        source contributions are not traced; each walk carries one summary contribution."""
+        hist = {}
+        trace, tlen, vals = res["trace"], res["trace_len"], res["walk_vals"]
+        has_neu = self.neumannBoundary is not None
+        for p in range(pts.shape[0]):
+            running, walks = 0.0, []
+            for w in range(W):
+                flat = p * W + w
+                path = [{"point": torch.tensor(trace[flat, k, :2]), "dirichlet_distance": float(trace[flat, k, 2]),
+                         "neumann_distance": float(trace[flat, k, 3]) if has_neu else None} for k in range(int(tlen[flat]))]
+                running += float(vals[p, w])
+                walks.append({"walk_id": w, "path": path,
+                              "contributions": [{"step": int(tlen[flat]), "type": "walk_total", "point": None, "contribution": float(vals[p, w])}],
+                              "total_contribution": running})
+            hist[p] = walks
+        return hist
