@@ -88,12 +88,13 @@ def cpu_baseline(n_threads=0, target_seconds=12.0):
     t0 = time.perf_counter()
     r = prob.solve(s.points[: 8 * cores], 16, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=1, n_threads=cores)
     rate = r["steps"] / (time.perf_counter() - t0)
-    n_pts = int(min(len(s.points), max(8 * cores, rate * target_seconds / (16.6 * 64))))
+    n_pts = len(s.points)
+    walks = int(max(16, rate * target_seconds / (16.6 * n_pts)))
     t0 = time.perf_counter()
-    r = prob.solve(s.points[:n_pts], 64, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=2, n_threads=cores)
+    r = prob.solve(s.points[:n_pts], walks, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=2, n_threads=cores)
     dt = time.perf_counter() - t0
     return {"value": r["steps"] / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_pts} points x 64 walks of the same scene ({r['steps']} steps in {dt:.2f} s), oracle/wost_oracle.c, OpenMP over points",
+            "sample": f"{n_pts} points x {walks} walks of the same scene ({r['steps']} steps in {dt:.2f} s), oracle/wost_oracle.c, OpenMP over points",
             "python_reference_probe": "the unmodified Python reference measured ~2.7e3 walk-steps/s on 1 core for this scene (BASELINE.md §2); it cannot travel to the GPU box"}
 
 
@@ -108,7 +109,12 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0))
     s = scenario(4096)
     prob = orc.Problem.from_scenario(s)
-    n_pts, walks = min(len(s.points), 64 * cores), 32
+    # calibrate so that one step is ~3 s of all-core CPU work
+    t0 = time.perf_counter()
+    r = prob.solve(s.points[: 8 * cores], 16, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=1, n_threads=cores)
+    rate = r["steps"] / (time.perf_counter() - t0)
+    n_pts = len(s.points)
+    walks = int(max(8, rate * 3.0 / (16.6 * n_pts)))
     t_steps, total = [], 0
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()

@@ -36,6 +36,7 @@ struct wost_scene {
     float4* nseg = nullptr;               // 2 float4 per Neumann segment
     int sm_count = 0;
     size_t smem_optin = 0;
+    float ndisc_x = 0.f, ndisc_y = 0.f, ndisc_r2 = 0.f;   // inflated disc enclosing the Neumann polyline
 };
 
 struct wost_field {
@@ -62,6 +63,8 @@ struct WalkArgs {
     unsigned long long* counter;           // next unassigned flat walk index
     unsigned long long* steps_total;
     int chunk;                             // walks a warp reserves per atomic
+    float ndisc_x, ndisc_y, ndisc_r2;      // disc enclosing the Neumann polyline (inflated), for ray culling
+    int coop_max;                          // cast rays cooperatively when at most this many lanes need one
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
 
@@ -129,93 +132,133 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        if (active) {
-            // ---- loop condition of the reference: tests the PREVIOUS step's dDirichlet (:206, Q5) ------
-            if (steps < a.max_steps && dD > a.eps) {
-                dD = dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);                 // :208
-                uint32_t o[4];
-                philox4x32_10(pidx, widx, (uint32_t)steps, 0u, a.key0, a.key1, o);
-                float theta = (u24(o[0]) * 2.0f) * 3.14159274101257324f;                // :226
-                if (NEU && onB) theta = theta / 2.0f + phi_n;                           // :227-228 (Q2)
-                float dy, dx; sincosf(theta, &dy, &dx);                                 // :230-232
+        // ---- this iteration: every active lane either takes one step of the reference's loop or terminates ----
+        // loop condition of the reference tests the PREVIOUS step's dDirichlet (:206, Q5)
+        const bool stepping = active && steps < a.max_steps && dD > a.eps;
+        if (active && !stepping) {
+            // terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7)
+            float bc = a.F.g.present ? field_eval(a.F.g, x, y) : 0.0f;
+            if (DELTA) bc = bc * atten;
+            a.walk_vals[id] = total_v + bc;
+            if (TRACE) { if ((long long)id < a.n_trace) a.trace_len[id] = min(steps, a.trace_cap); }
+            steps_acc += (unsigned long long)steps;
+            active = false;
+        }
 
-                float dN = CUDART_INF_F, r, qx, qy;
-                if (NEU) {
-                    // intersect_polylines_jit prologue (:149-159): normalise, offset the origin by 1e-6
-                    const float dn = norm2(dx, dy);
-                    const float ex = dx / dn, ey = dy / dn;
-                    const float ox = x + 1e-6f * ex, oy = y + 1e-6f * ey;
-                    const NeumannQuery nq = neumann_pass<true>(nseg, a.n_nseg, x, y, ox, oy, ex, ey);
-                    dN = nq.sil_d;                                                       // :211
-                    const float m = dN < dD ? dN : dD;                                   // :212
-                    r = (m > a.rmin) ? m : a.rmin;
-                    if (nq.best_k < 0 || nq.best_s > r || nq.best_s <= 0.0f) {           // :166-174 miss
-                        qx = x + r * ex; qy = y + r * ey; onB = false;
-                    } else {                                                             // :176-197 hit
-                        qx = ox + nq.best_s * ex; qy = oy + nq.best_s * ey; onB = true;
-                        phi_n = nseg[2 * nq.best_k + 1].z;                               // atan2 of the left normal (Q3)
-                    }
-                } else {
-                    r = (dD > a.rmin) ? dD : a.rmin;                                     // :215
-                    qx = x + r * dx; qy = y + r * dy; onB = false;                       // :238-239
-                }
-                if (TRACE) {
-                    if ((long long)id < a.n_trace && steps < a.trace_cap) {
-                        float4* t = reinterpret_cast<float4*>(a.trace) + (size_t)id * a.trace_cap + steps;
-                        *t = make_float4(x, y, dD, dN);
-                    }
-                }
-
-                float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f;
-                if (DELTA) {
-                    sbgn = interior_probability(r * a.sqrt_sigma_bar);                   // sigma_bar * |G^sb|(r)
-                    gn = sbgn * a.inv_sigma_bar;                                         // screenedGreensNorm2D (utils.py:29-44)
-                }
-                if (SRC || DELTA) {                                                      // :242 (Q10: also without a source)
-                    float rho;
-                    if (DELTA) {                                                         // screened radius: inverse-CDF table (Q9)
-                        const float pos = u24(o[2]) * (float)(a.icdf_len - 1);
-                        int i = min((int)pos, a.icdf_len - 2);
-                        const float fr = pos - (float)i;
-                        const float t0 = __ldg(a.icdf + i), t1 = __ldg(a.icdf + i + 1);
-                        rho = t0 + fr * (t1 - t0);
-                    } else {                                                             // pdf -ln(rho): product of two uniforms (Q8)
-                        rho = fmaxf(u24p(o[2]) * u24p(o[3]), 1e-6f);
-                    }
-                    const float rs = rho * r;                                            // utils.py:117
-                    sx = x + rs * dx; sy = y + rs * dy;                                  // :245
-                    float contrib = 0.0f;
-                    if (norm2(sx - x, sy - y) > norm2(qx - x, qy - y)) {                 // :248-250
-                        sx = qx; sy = qy;
-                    } else if (SRC) {
-                        if (DELTA)                                                       // :252-254
-                            contrib = (field_eval(a.F.f, sx, sy) * gn / sqrtf(alpha_at(a.F, sx, sy) * alpha_at(a.F, x, y))) * atten;
-                        else
-                            contrib = field_eval(a.F.f, sx, sy) * (r * r / 4.0f);        // :256
-                    }
-                    if (SRC) total_v += contrib;                                         // :258
-                }
-                if (DELTA) {                                                             // :271-284
-                    if (u24(o[1]) > sbgn) {
-                        atten = atten * sqrtf(alpha_at(a.F, qx, qy) / alpha_at(a.F, x, y));
-                        x = qx; y = qy;
-                    } else {
-                        const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy);
-                        const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);
-                        atten = (atten * sqrtf(alpha_at(a.F, sx, sy) / alpha_at(a.F, x, y))) * sc;
-                        x = sx; y = sy;
-                    }
-                } else { x = qx; y = qy; }                                               // :287
-                ++steps;                                                                 // :291
+        // ---- phase A: distances, star radius, direction ------------------------------------------------------
+        float dN = CUDART_INF_F, r = 0.f, dx = 0.f, dy = 0.f, ex = 0.f, ey = 0.f, ox = 0.f, oy = 0.f;
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+        bool want_ray = false;
+        if (stepping) {
+            dD = dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);                     // :208
+            uint32_t w0;
+            if (!SRC && !DELTA) {
+                // Laplace walks use one 32-bit word per step: one Philox block serves four steps
+                philox4x32_10(pidx, widx, (uint32_t)steps >> 2, 1u, a.key0, a.key1, o);
+                const int sel = steps & 3;
+                w0 = sel == 0 ? o[0] : (sel == 1 ? o[1] : (sel == 2 ? o[2] : o[3]));
             } else {
-                // ---- terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7) --------
-                float bc = a.F.g.present ? field_eval(a.F.g, x, y) : 0.0f;
-                if (DELTA) bc = bc * atten;
-                a.walk_vals[id] = total_v + bc;
-                if (TRACE) { if ((long long)id < a.n_trace) a.trace_len[id] = min(steps, a.trace_cap); }
-                steps_acc += (unsigned long long)steps;
-                active = false;
+                philox4x32_10(pidx, widx, (uint32_t)steps, 0u, a.key0, a.key1, o);
+                w0 = o[0];
             }
+            float theta = (u24(w0) * 2.0f) * 3.14159274101257324f;                      // :226
+            if (NEU && onB) theta = theta / 2.0f + phi_n;                               // :227-228 (Q2)
+            sincosf(theta, &dy, &dx);                                                   // :230-232
+            if (NEU) {
+                dN = sqrtf(silhouette_distance_sq(nseg, a.n_nseg, x, y));               // :211
+                const float m = dN < dD ? dN : dD;                                      // :212
+                r = (m > a.rmin) ? m : a.rmin;
+                // intersect_polylines_jit prologue (:149-159): normalise, offset the origin by 1e-6
+                const float dn = norm2(dx, dy);
+                ex = dx / dn; ey = dy / dn;
+                ox = x + 1e-6f * ex; oy = y + 1e-6f * ey;
+                want_ray = ray_may_hit_disc(ox, oy, ex, ey, a.ndisc_x, a.ndisc_y, a.ndisc_r2);
+            } else {
+                r = (dD > a.rmin) ? dD : a.rmin;                                        // :215
+            }
+        }
+
+        // ---- phase B: ray vs Neumann polyline (:162-178) -------------------------------------------------------
+        // Rays that cannot reach the polyline's bounding disc are culled; the rest are cast either per lane or, when
+        // only a few lanes of the warp need one, cooperatively (32 segments per instruction for one ray).
+        float best_s = CUDART_INF_F; int best_k = -1;
+        if (NEU) {
+            unsigned rays = __ballot_sync(FULL, want_ray);
+            if (__popc(rays) > a.coop_max) {
+                if (want_ray) ray_cast(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
+            } else {
+                while (rays) {
+                    const int src = __ffs(rays) - 1; rays &= rays - 1u;
+                    const float box = __shfl_sync(FULL, ox, src), boy = __shfl_sync(FULL, oy, src);
+                    const float bex = __shfl_sync(FULL, ex, src), bey = __shfl_sync(FULL, ey, src);
+                    float cs; int ck;
+                    ray_cast_coop(nseg, a.n_nseg, box, boy, bex, bey, lane, cs, ck);
+                    if (lane == src) { best_s = cs; best_k = ck; }
+                }
+            }
+        }
+
+        // ---- phase C: move, source sample, delta tracking ---------------------------------------------------------
+        if (stepping) {
+            float qx, qy;
+            if (NEU) {
+                if (best_k < 0 || best_s > r || best_s <= 0.0f) {                       // :166-174 miss
+                    qx = x + r * ex; qy = y + r * ey; onB = false;
+                } else {                                                                // :176-197 hit
+                    qx = ox + best_s * ex; qy = oy + best_s * ey; onB = true;
+                    phi_n = nseg[2 * best_k + 1].z;                                     // atan2 of the left normal (Q3)
+                }
+            } else {
+                qx = x + r * dx; qy = y + r * dy; onB = false;                          // :238-239
+            }
+            if (TRACE) {
+                if ((long long)id < a.n_trace && steps < a.trace_cap) {
+                    float4* t = reinterpret_cast<float4*>(a.trace) + (size_t)id * a.trace_cap + steps;
+                    *t = make_float4(x, y, dD, dN);
+                }
+            }
+
+            float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f;
+            if (DELTA) {
+                sbgn = interior_probability(r * a.sqrt_sigma_bar);                      // sigma_bar * |G^sb|(r)
+                gn = sbgn * a.inv_sigma_bar;                                            // screenedGreensNorm2D (utils.py:29-44)
+            }
+            if (SRC || DELTA) {                                                         // :242 (Q10: also without a source)
+                float rho;
+                if (DELTA) {                                                            // screened radius: inverse-CDF table (Q9)
+                    const float pos = u24(o[2]) * (float)(a.icdf_len - 1);
+                    int i = min((int)pos, a.icdf_len - 2);
+                    const float fr = pos - (float)i;
+                    const float t0 = __ldg(a.icdf + i), t1 = __ldg(a.icdf + i + 1);
+                    rho = t0 + fr * (t1 - t0);
+                } else {                                                                // pdf -ln(rho): product of two uniforms (Q8)
+                    rho = fmaxf(u24p(o[2]) * u24p(o[3]), 1e-6f);
+                }
+                const float rs = rho * r;                                               // utils.py:117
+                sx = x + rs * dx; sy = y + rs * dy;                                     // :245
+                float contrib = 0.0f;
+                if (norm2(sx - x, sy - y) > norm2(qx - x, qy - y)) {                    // :248-250
+                    sx = qx; sy = qy;
+                } else if (SRC) {
+                    if (DELTA)                                                          // :252-254
+                        contrib = (field_eval(a.F.f, sx, sy) * gn / sqrtf(alpha_at(a.F, sx, sy) * alpha_at(a.F, x, y))) * atten;
+                    else
+                        contrib = field_eval(a.F.f, sx, sy) * (r * r / 4.0f);           // :256
+                }
+                if (SRC) total_v += contrib;                                            // :258
+            }
+            if (DELTA) {                                                                // :271-284
+                if (u24(o[1]) > sbgn) {
+                    atten = atten * sqrtf(alpha_at(a.F, qx, qy) / alpha_at(a.F, x, y));
+                    x = qx; y = qy;
+                } else {
+                    const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy);
+                    const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);
+                    atten = (atten * sqrtf(alpha_at(a.F, sx, sy) / alpha_at(a.F, x, y))) * sc;
+                    x = sx; y = sy;
+                }
+            } else { x = qx; y = qy; }                                                  // :287
+            ++steps;                                                                    // :291
         }
     }
     // total step count: warp reduce, one atomic per warp
@@ -310,12 +353,7 @@ __global__ void geom_ray_kernel(SegView sv, const float* p, const float* dir, lo
     if (i >= B) return;
     const float ox = p[2 * i], oy = p[2 * i + 1], ex = dir[2 * i], ey = dir[2 * i + 1];
     for (int k = 0; k < sv.n; ++k) {
-        const float4 s0 = seg_au(sv, k);
-        const float wx = ox - s0.x, wy = oy - s0.y;
-        const float d = ex * s0.w - ey * s0.z;
-        const float s = (ex * wy - ey * wx) / d;
-        const float t = (s0.z * wy - s0.w * wx) / d;
-        out_s[i * (long long)sv.n + k] = (s >= 0.0f && s <= 1.0f && t > 0.0f) ? s : CUDART_INF_F;
+        out_s[i * (long long)sv.n + k] = ray_segment_s(seg_au(sv, k), ox, oy, ex, ey);
     }
 }
 
@@ -330,11 +368,12 @@ __global__ void geom_intersect_kernel(const float4* nseg, int n, const float* p,
     else {
         const float ex = dx / dn, ey = dy / dn;
         const float ox = x + 1e-6f * ex, oy = y + 1e-6f * ey;
-        const NeumannQuery nq = neumann_pass<true>(nseg, n, x, y, ox, oy, ex, ey);
-        if (nq.best_k < 0 || nq.best_s > r || nq.best_s <= 0.0f) { qx = x + r * ex; qy = y + r * ey; nx = ny = 0.0f; }
+        float best_s; int best_k;
+        ray_cast(nseg, n, ox, oy, ex, ey, best_s, best_k);
+        if (best_k < 0 || best_s > r || best_s <= 0.0f) { qx = x + r * ex; qy = y + r * ey; nx = ny = 0.0f; }
         else {
-            qx = ox + nq.best_s * ex; qy = oy + nq.best_s * ey;
-            const float4 s1 = nseg[2 * nq.best_k + 1]; nx = s1.x; ny = s1.y; found = 1; segk = nq.best_k;
+            qx = ox + best_s * ex; qy = oy + best_s * ey;
+            const float4 s1 = nseg[2 * best_k + 1]; nx = s1.x; ny = s1.y; found = 1; segk = best_k;
         }
     }
     if (out_pt) { out_pt[2 * i] = qx; out_pt[2 * i + 1] = qy; }
@@ -513,6 +552,19 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         cudaFree(s->dseg); cudaFree(s->nseg); delete s;
         return fail(WOST_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
     }
+    if (nn > 0) {
+        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+        for (int k = 0; k < nn; ++k) {
+            xmin = std::fmin(xmin, nxy[2 * k]); xmax = std::fmax(xmax, nxy[2 * k]);
+            ymin = std::fmin(ymin, nxy[2 * k + 1]); ymax = std::fmax(ymax, nxy[2 * k + 1]);
+        }
+        const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
+        double r2 = 0.0;
+        for (int k = 0; k < nn; ++k) r2 = std::fmax(r2, (nxy[2 * k] - cx) * (nxy[2 * k] - cx) + (nxy[2 * k + 1] - cy) * (nxy[2 * k + 1] - cy));
+        const double scale = std::fmax(std::fmax(std::fabs(xmin), std::fabs(xmax)), std::fmax(std::fabs(ymin), std::fabs(ymax)));
+        const double R = std::sqrt(r2) * 1.001 + 1e-4 * scale + 1e-30;   // slack: fp32 rounding of s, t and of the cull itself
+        s->ndisc_x = (float)cx; s->ndisc_y = (float)cy; s->ndisc_r2 = (float)(R * R);
+    }
     tune_pool(device);
     *out = s;
     return WOST_OK;
@@ -685,6 +737,8 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     a.key0 = (uint32_t)P->seed; a.key1 = (uint32_t)(P->seed >> 32);
     a.point_index_base = P->point_index_base; a.walk_offset = P->walk_offset;
     a.walk_vals = vals; a.counter = ctrs; a.steps_total = ctrs + 1;
+    a.ndisc_x = scene->ndisc_x; a.ndisc_y = scene->ndisc_y; a.ndisc_r2 = scene->ndisc_r2;
+    a.coop_max = scene->n_nseg >= 8 ? 12 : 0;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;

@@ -33,16 +33,11 @@ except ImportError:  # pragma: no cover - reference-style sys.path layout (solve
 
 SP_FULL, SP_RATIO, SP_FIELD = nat.SP_FULL, nat.SP_RATIO, nat.SP_FIELD
 
-_seed_state = {"initial": None, "calls": 0}
-
-
 def _next_seed() -> int:
-    """A fresh Philox key per solve() derived from torch's global seed, so that re-seeding torch replays a script."""
-    init = torch.initial_seed()
-    if _seed_state["initial"] != init:
-        _seed_state["initial"], _seed_state["calls"] = init, 0
-    _seed_state["calls"] += 1
-    return (init * 0x9E3779B97F4A7C15 + _seed_state["calls"] * 0xD1B54A32D192ED03) % (1 << 64)
+    """A fresh Philox key per solve(), drawn from torch's global CPU generator — the stream the reference consumes
+    with torch.rand (solvers/WoStSolver.py:226) — so torch.manual_seed(42) replays a script and successive solves differ."""
+    hi, lo = torch.randint(0, 1 << 31, (2,), dtype=torch.int64).tolist()
+    return (hi << 31) | lo
 
 
 def _zero_boundary(point):

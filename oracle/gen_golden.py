@@ -198,7 +198,7 @@ def gen_walks(PolyLinesSimple, WostSolver_2D, only=None):
 
     # (scenario key, evaluation-point subset, walks) sized so the whole script stays within minutes
     plan = {"cfg1a": (slice(None), 150), "cfg1b": (slice(None), 40), "cfg2": (slice(0, 404, 9), 100),
-            "cfg3": (slice(0, 404, 9), 100), "cfg4": (slice(0, 648, 18), 25), "cfg5": (slice(0, 9, 2), 30)}
+            "cfg3": (slice(0, 404, 9), 100), "cfg4": (slice(0, 648, 18), 25), "cfg5": (slice(0, 9, 2), 150)}
     for key, (sub, W) in plan.items():
         if only and key not in only:
             continue

@@ -501,7 +501,10 @@ static float run_walk(const orc_params_t* p, walk_rng_t* g, float x0, float y0, 
 
         float u_theta, u_mu = 0.0f;
         if (g->mode == ORC_RNG_MT) u_theta = mt_torch_rand(g->torch_rng);   /* :226 */
-        else { orc_philox4x32_10(pidx, widx, (uint32_t)steps, 0u, g->k0, g->k1, g->o); u_theta = u24(g->o[0]); u_mu = u24(g->o[1]); }
+        else if (!has_src && !p->delta) {
+            /* Laplace walks need one 32-bit word per step: one Philox block (stream tag 1) serves four steps */
+            orc_philox4x32_10(pidx, widx, (uint32_t)steps >> 2, 1u, g->k0, g->k1, g->o); u_theta = u24(g->o[steps & 3]);
+        } else { orc_philox4x32_10(pidx, widx, (uint32_t)steps, 0u, g->k0, g->k1, g->o); u_theta = u24(g->o[0]); u_mu = u24(g->o[1]); }
         float theta = (u_theta * 2.0f) * 3.14159274101257324f;       /* :226 fp32 */
         if (onB && has_neu) theta = theta / 2.0f + (p->atan2_fn ? p->atan2_fn(ny, nx) : atan2f(ny, nx));   /* :227-228 (Q2) */
         float dx, dy;                                                /* :230-232 */

@@ -163,8 +163,10 @@ def test_walks_match_oracle_per_walk(key):
     o = prob.solve(pts, W, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=1234, icdf=icdf, walk_vals=True, walk_steps=True,
                    n_trace=len(pts) * W, trace_cap=8)
     n3 = np.minimum(np.minimum(r["trace_len"], o["trace_len"]), 3)
+    lim = float(s.dirichlet.abs().max())
     for i in range(len(n3)):
-        assert np.allclose(r["trace"][i, : n3[i]], o["trace"][i, : n3[i]], rtol=1e-5, atol=1e-6), (key, i)
+        # 1e-5 of the coordinate scale (distances are differences of coordinates)
+        assert np.allclose(r["trace"][i, : n3[i]], o["trace"][i, : n3[i]], rtol=1e-5, atol=1e-5 * lim), (key, i)
     same_len = r["trace_len"] == o["trace_len"]
     assert same_len.mean() > 0.9
     dv = np.abs(r["walk_vals"] - o["walk_vals"])
@@ -183,13 +185,34 @@ def test_estimates_within_3_sigma_of_reference(golden, key):
     solver = s.make_solver()
     nw = 20000
     r = solver.solve_raw(W["points"], nw, int(W["max_steps"]), float(W["eps"]), seed=99)
-    se_gpu = np.sqrt(r["m2"] / (nw - 1) / nw)
+    var_gpu = r["m2"] / (nw - 1)
+    se_gpu = np.sqrt(var_gpu / nw)
     n_ref = int(W["n_walks"])
-    ref_mean, se_ref = W["walk_vals"].mean(axis=1), W["walk_vals"].std(axis=1, ddof=1) / np.sqrt(n_ref)
+    ref_mean = W["walk_vals"].mean(axis=1)
+    # standard error of the reference's n_ref-walk mean.  Under the hypothesis being tested both draw from the same
+    # per-walk distribution, whose variance the 20000 GPU walks estimate far better than the reference's few dozen
+    # (cfg5's per-walk values are heavy-tailed: most walks contribute ~0, a few carry the whole estimate).
+    se_ref = np.sqrt(var_gpu / n_ref)
     z = (r["mean"] - ref_mean) / np.sqrt(se_gpu ** 2 + se_ref ** 2 + 1e-30)
     assert np.mean(np.abs(z) <= 3.0) >= 0.95, z
     assert abs(np.mean(z)) < 4.0 / np.sqrt(len(z)) + 0.35
     assert abs(int(r["steps"][0]) / (nw * len(W["points"])) / W["walk_steps"].mean() - 1.0) < 0.08
+
+
+@pytest.mark.parametrize("key,nw", [("cfg4", 6000), ("cfg5", 6000)])
+def test_estimates_match_replayed_reference_at_matched_walk_counts(key, nw):
+    """The two scenarios without an analytic solution, at matched (large) walk counts: the oracle in mt19937-replay
+    mode IS the reference's estimator (same streams, same sample caches; pinned step for step in
+    tests/test_oracle_pinned.py), so its estimate at nw walks stands in for a reference run that would take hours."""
+    s = sc.ALL[key]()
+    solver = s.make_solver()
+    pts = s.points[:: max(1, len(s.points) // 6)][:6].contiguous()
+    r = solver.solve_raw(pts, nw, s.max_steps, s.eps, seed=31)
+    o = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar).solve(pts, nw, s.max_steps, s.eps, rng_mode=orc.RNG_MT, seed=5, seed_numpy=5)
+    se_gpu = np.sqrt(r["m2"] / (nw - 1) / nw)
+    z = (r["mean"] - o["mean"]) / np.sqrt(se_gpu ** 2 + o["stderr"] ** 2 + 1e-30)
+    assert np.all(np.abs(z) <= 3.5), z
+    assert abs(int(r["steps"][0]) / o["steps"] - 1.0) < 0.05
 
 
 @pytest.mark.parametrize("key,nw", [("cfg1a", 100000), ("cfg1b", 100000), ("cfg3", 100000)])
