@@ -1,0 +1,98 @@
+"""Host-side logic of the multi-GPU path, exercised with world_size 2 and 3 over gloo on the CPU.
+
+The walk kernel itself needs a GPU; here a stand-in solver produces per-walk values from the GLOBAL (point, walk)
+indices — exactly the property the real kernel has through its Philox counters — so that the shard plan, the
+gathers and the block-ordered merge can be checked to be independent of the number of ranks.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dcrmontecarlo_b200.distributed import WALK_BLOCK, shard_plan, solve_sharded
+
+
+def walk_value(p, w, seed):
+    """Deterministic stand-in for one walk's total, a function of global indices only."""
+    h = (p * 2654435761 + w * 40503 + seed * 97) % 1000003
+    return np.float32(h / 1000003.0 - 0.5 + 0.001 * p)
+
+
+def block_stats(vals):
+    P, W = vals.shape
+    nblk = (W + WALK_BLOCK - 1) // WALK_BLOCK
+    out = np.zeros((P, nblk, 2))
+    for b in range(nblk):
+        v = vals[:, b * WALK_BLOCK:(b + 1) * WALK_BLOCK].astype(np.float64)
+        m = v.mean(axis=1)
+        out[:, b, 0], out[:, b, 1] = m, ((v - m[:, None]) ** 2).sum(axis=1)
+    return out
+
+
+def merge_blocks(blocks, n_walks):
+    blocks = blocks.numpy() if isinstance(blocks, torch.Tensor) else blocks
+    P, nblk, _ = blocks.shape
+    na, ma, qa = np.zeros(P), np.zeros(P), np.zeros(P)
+    for b in range(nblk):
+        nb = float(min(WALK_BLOCK, n_walks - b * WALK_BLOCK))
+        mb, qb = blocks[:, b, 0], blocks[:, b, 1]
+        n = na + nb
+        d = mb - ma
+        ma = ma + d * (nb / n)
+        qa = qa + qb + (d * d) * (na * nb / n)
+        na = n
+    return ma, qa
+
+
+class FakeSolver:
+    def solve_raw(self, pts, nWalks, maxSteps, eps, *, seed, point_index_base, walk_offset, want_block_stats, device_outputs):
+        P = len(pts)
+        vals = np.array([[walk_value(point_index_base + p, walk_offset + w, seed) for w in range(nWalks)] for p in range(P)], np.float32)
+        bs = block_stats(vals)
+        mean, m2 = merge_blocks(bs, nWalks)
+        return dict(mean=mean, m2=m2, block_stats=bs, steps=np.array([P * nWalks * 3], np.uint64), n=nWalks)
+
+
+def _worker(rank, world, port, P, W, mode, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pts = torch.arange(2 * P, dtype=torch.float32).reshape(P, 2)
+    r = solve_sharded(FakeSolver(), pts, W, seed=11, mode=mode, merge_fn=merge_blocks)
+    if rank == world - 1:                                              # every rank holds the full result; check the last one
+        ret["mean"], ret["m2"], ret["steps"] = r["mean"].numpy().copy(), r["m2"].numpy().copy(), r["steps"]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,P,W,mode", [(2, 7, 300, "auto"), (3, 5, 200, "points"), (2, 1, 3000, "auto"), (3, 2, 2500, "walks")])
+def test_sharded_solve_is_independent_of_rank_count(world, P, W, mode):
+    single = FakeSolver().solve_raw(np.zeros((P, 2)), W, 0, 0, seed=11, point_index_base=0, walk_offset=0,
+                                    want_block_stats=True, device_outputs=False)
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), P, W, mode, ret), nprocs=world, join=True)
+    assert np.array_equal(ret["mean"], single["mean"]) and np.array_equal(ret["m2"], single["m2"])   # bit-identical
+    assert ret["steps"] == P * W * 3
+
+
+def test_shard_plan_covers_everything_once():
+    for P, W, world in [(404, 150, 8), (9, 100, 8), (9, 5000, 8), (1, 1, 4), (65536, 256, 8), (3, 4096, 2)]:
+        plan = shard_plan(P, W, world)
+        assert len(plan) == world
+        seen = np.zeros((P, W), np.int32)
+        for sh in plan:
+            seen[sh.p0:sh.p1, sh.w0:sh.w1] += 1
+            assert sh.n_walks == 0 or sh.w0 % WALK_BLOCK == 0          # walk shards start on reduction-block boundaries
+        assert np.all(seen == 1)
+        if P >= world:
+            assert all(sh.w0 == 0 and sh.w1 == W for sh in plan)
+            assert max(sh.n_points for sh in plan) - min(sh.n_points for sh in plan) <= 1
