@@ -36,7 +36,7 @@ struct wost_scene {
     float4* nseg = nullptr;               // 2 float4 per Neumann segment
     int sm_count = 0;
     size_t smem_optin = 0;
-    float ndisc_x = 0.f, ndisc_y = 0.f, ndisc_r2 = 0.f;   // inflated disc enclosing the Neumann polyline
+    float ndisc_x = 0.f, ndisc_y = 0.f, ndisc_r = 0.f, ndisc_r2 = 0.f;   // inflated disc enclosing the Neumann polyline
 };
 
 struct wost_field {
@@ -63,8 +63,8 @@ struct WalkArgs {
     unsigned long long* counter;           // next unassigned flat walk index
     unsigned long long* steps_total;
     int chunk;                             // walks a warp reserves per atomic
-    float ndisc_x, ndisc_y, ndisc_r2;      // disc enclosing the Neumann polyline (inflated), for ray culling
-    int coop_max;                          // cast rays cooperatively when at most this many lanes need one
+    float ndisc_x, ndisc_y, ndisc_r, ndisc_r2;   // disc enclosing the Neumann polyline (inflated), for culling
+    int sil_coop_max, ray_coop_max;        // answer a query cooperatively when at most this many lanes need it
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
 
@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
     float x = 0.f, y = 0.f, dD = 1.0f, atten = 1.0f, total_v = 0.0f, phi_n = 0.0f;
     bool onB = false; int steps = 0;
     unsigned long long steps_acc = 0;
+    uint32_t o[4] = {0u, 0u, 0u, 0u};          // Philox block (kept across steps: Laplace walks use one word per step)
+    const float4 nseg0 = (NEU && lane < a.n_nseg) ? a.nseg[2 * lane] : make_float4(0.f, 0.f, 0.f, 0.f);   // segment `lane`, register-resident
 
     while (true) {
         // ---- regeneration ------------------------------------------------------------------------
@@ -145,17 +147,16 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
             active = false;
         }
 
-        // ---- phase A: distances, star radius, direction ------------------------------------------------------
+        // ---- phase A: Dirichlet distance, direction --------------------------------------------------------------
         float dN = CUDART_INF_F, r = 0.f, dx = 0.f, dy = 0.f, ex = 0.f, ey = 0.f, ox = 0.f, oy = 0.f;
-        uint32_t o[4] = {0u, 0u, 0u, 0u};
-        bool want_ray = false;
+        bool want_ray = false, want_sil = false;
         if (stepping) {
             dD = dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);                     // :208
             uint32_t w0;
             if (!SRC && !DELTA) {
-                // Laplace walks use one 32-bit word per step: one Philox block serves four steps
-                philox4x32_10(pidx, widx, (uint32_t)steps >> 2, 1u, a.key0, a.key1, o);
+                // Laplace walks use one 32-bit word per step: one Philox block (stream tag 1) serves four steps
                 const int sel = steps & 3;
+                if (sel == 0) philox4x32_10(pidx, widx, (uint32_t)steps >> 2, 1u, a.key0, a.key1, o);
                 w0 = sel == 0 ? o[0] : (sel == 1 ? o[1] : (sel == 2 ? o[2] : o[3]));
             } else {
                 philox4x32_10(pidx, widx, (uint32_t)steps, 0u, a.key0, a.key1, o);
@@ -165,37 +166,57 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
             if (NEU && onB) theta = theta / 2.0f + phi_n;                               // :227-228 (Q2)
             sincosf(theta, &dy, &dx);                                                   // :230-232
             if (NEU) {
-                dN = sqrtf(silhouette_distance_sq(nseg, a.n_nseg, x, y));               // :211
-                const float m = dN < dD ? dN : dD;                                      // :212
-                r = (m > a.rmin) ? m : a.rmin;
                 // intersect_polylines_jit prologue (:149-159): normalise, offset the origin by 1e-6
                 const float dn = norm2(dx, dy);
                 ex = dx / dn; ey = dy / dn;
                 ox = x + 1e-6f * ex; oy = y + 1e-6f * ey;
                 want_ray = ray_may_hit_disc(ox, oy, ex, ey, a.ndisc_x, a.ndisc_y, a.ndisc_r2);
-            } else {
-                r = (dD > a.rmin) ? dD : a.rmin;                                        // :215
+                // the silhouette distance only matters if it can be smaller than dDirichlet (:212): every Neumann
+                // vertex is at least (|p - c| - R) away, so outside that margin min(dD, dN) = dD without looking.
+                const float gx = x - a.ndisc_x, gy = y - a.ndisc_y;
+                const float gap = sqrtf(gx * gx + gy * gy) - a.ndisc_r;
+                want_sil = TRACE || !(dD < gap * 0.9999f);
             }
         }
 
-        // ---- phase B: ray vs Neumann polyline (:162-178) -------------------------------------------------------
-        // Rays that cannot reach the polyline's bounding disc are culled; the rest are cast either per lane or, when
-        // only a few lanes of the warp need one, cooperatively (32 segments per instruction for one ray).
+        // ---- phase B: queries against the Neumann polyline -------------------------------------------------------------
+        // Each query is answered per lane (a loop over all segments) when most lanes of the warp need it, or
+        // warp-cooperatively (32 segments per instruction for one query) when only a few do.
         float best_s = CUDART_INF_F; int best_k = -1;
         if (NEU) {
-            unsigned rays = __ballot_sync(FULL, want_ray);
-            if (__popc(rays) > a.coop_max) {
-                if (want_ray) ray_cast(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
+            const bool small = a.n_nseg <= 32;                                          // warp-uniform
+            float dN2 = CUDART_INF_F;                                                   // squared; rooted once below
+            unsigned need = __ballot_sync(FULL, want_sil);                              // silhouette distance (:211)
+            if (__popc(need) > a.sil_coop_max) {
+                if (want_sil) dN2 = silhouette_distance_sq(nseg, a.n_nseg, x, y);
             } else {
-                while (rays) {
-                    const int src = __ffs(rays) - 1; rays &= rays - 1u;
-                    const float box = __shfl_sync(FULL, ox, src), boy = __shfl_sync(FULL, oy, src);
-                    const float bex = __shfl_sync(FULL, ex, src), bey = __shfl_sync(FULL, ey, src);
-                    float cs; int ck;
-                    ray_cast_coop(nseg, a.n_nseg, box, boy, bex, bey, lane, cs, ck);
-                    if (lane == src) { best_s = cs; best_k = ck; }
+                while (need) {
+                    const int src = __ffs(need) - 1; need &= need - 1u;
+                    const float qx_ = __shfl_sync(FULL, x, src), qy_ = __shfl_sync(FULL, y, src);
+                    const float q = small ? silhouette_distance_sq_coop<true>(nseg, a.n_nseg, nseg0, qx_, qy_, lane)
+                                          : silhouette_distance_sq_coop<false>(nseg, a.n_nseg, nseg0, qx_, qy_, lane);
+                    dN2 = lane == src ? q : dN2;
                 }
             }
+            dN = sqrtf(dN2);
+            need = __ballot_sync(FULL, want_ray);                                       // ray vs polyline (:162-178)
+            if (__popc(need) > a.ray_coop_max) {
+                if (want_ray) ray_cast(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
+            } else {
+                while (need) {
+                    const int src = __ffs(need) - 1; need &= need - 1u;
+                    const float rox = __shfl_sync(FULL, ox, src), roy = __shfl_sync(FULL, oy, src);
+                    const float rex = __shfl_sync(FULL, ex, src), rey = __shfl_sync(FULL, ey, src);
+                    float cs; int ck;
+                    if (small) ray_cast_coop<true>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
+                    else ray_cast_coop<false>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
+                    best_s = lane == src ? cs : best_s; best_k = lane == src ? ck : best_k;
+                }
+            }
+        }
+        if (stepping) {
+            if (NEU) { const float m = dN < dD ? dN : dD; r = (m > a.rmin) ? m : a.rmin; }   // :212
+            else r = (dD > a.rmin) ? dD : a.rmin;                                       // :215
         }
 
         // ---- phase C: move, source sample, delta tracking ---------------------------------------------------------
@@ -563,7 +584,7 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         for (int k = 0; k < nn; ++k) r2 = std::fmax(r2, (nxy[2 * k] - cx) * (nxy[2 * k] - cx) + (nxy[2 * k + 1] - cy) * (nxy[2 * k + 1] - cy));
         const double scale = std::fmax(std::fmax(std::fabs(xmin), std::fabs(xmax)), std::fmax(std::fabs(ymin), std::fabs(ymax)));
         const double R = std::sqrt(r2) * 1.001 + 1e-4 * scale + 1e-30;   // slack: fp32 rounding of s, t and of the cull itself
-        s->ndisc_x = (float)cx; s->ndisc_y = (float)cy; s->ndisc_r2 = (float)(R * R);
+        s->ndisc_x = (float)cx; s->ndisc_y = (float)cy; s->ndisc_r = (float)R; s->ndisc_r2 = (float)(R * R);
     }
     tune_pool(device);
     *out = s;
@@ -737,8 +758,15 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     a.key0 = (uint32_t)P->seed; a.key1 = (uint32_t)(P->seed >> 32);
     a.point_index_base = P->point_index_base; a.walk_offset = P->walk_offset;
     a.walk_vals = vals; a.counter = ctrs; a.steps_total = ctrs + 1;
-    a.ndisc_x = scene->ndisc_x; a.ndisc_y = scene->ndisc_y; a.ndisc_r2 = scene->ndisc_r2;
-    a.coop_max = scene->n_nseg >= 8 ? 12 : 0;
+    a.ndisc_x = scene->ndisc_x; a.ndisc_y = scene->ndisc_y; a.ndisc_r = scene->ndisc_r; a.ndisc_r2 = scene->ndisc_r2;
+    {   // instruction-count model: per-lane loop ~12 (silhouette) / ~20 (ray) per segment for the whole warp;
+        // cooperative ~14 / ~16 per 32-segment chunk plus ~10 per query
+        const int n = scene->n_nseg, chunks = (n + 31) / 32;
+        a.sil_coop_max = n >= 8 ? (12 * n) / (14 * chunks + 10) : 0;
+        a.ray_coop_max = n >= 8 ? (20 * n) / (16 * chunks + 14) : 0;
+        if (a.sil_coop_max > 32) a.sil_coop_max = 32;
+        if (a.ray_coop_max > 32) a.ray_coop_max = 32;
+    }
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;
