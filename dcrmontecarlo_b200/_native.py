@@ -6,6 +6,7 @@ is made, a RuntimeError is raised.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from pathlib import Path
 
@@ -13,7 +14,7 @@ import numpy as np
 import torch
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libwost.so"
+LIB_PATH = Path(os.environ.get("WOST_LIB", PKG / "libwost.so"))   # WOST_LIB: alternative build (A/B experiments)
 
 WALK_BLOCK = 1024
 SP_FULL, SP_RATIO, SP_FIELD = 0, 1, 2

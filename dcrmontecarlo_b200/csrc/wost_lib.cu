@@ -75,7 +75,7 @@ struct WalkArgs {
 //
 // The loop body restates solvers/WoStSolver.py:206-298 of the reference, quirks included.
 template <bool NEU, bool SRC, bool DELTA, bool TRACE>
-__global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
+__global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
     extern __shared__ float4 smem[];
     const float4* dseg = a.dseg; const float4* nseg = a.nseg;
     if (a.stage_smem) {
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
     bool active = false, retired = false;
     unsigned long long id = 0; uint32_t pidx = 0, widx = 0;
     float x = 0.f, y = 0.f, dD = 1.0f, atten = 1.0f, total_v = 0.0f, phi_n = 0.0f;
+    float alpha_x = 1.0f;                      // alpha at the walker's position (delta tracking), carried from step to step
     bool onB = false; int steps = 0;
     unsigned long long steps_acc = 0;
     uint32_t o[4] = {0u, 0u, 0u, 0u};          // Philox block (kept across steps: Laplace walks use one word per step)
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
                 x = __ldg(a.pts + 2 * p); y = __ldg(a.pts + 2 * p + 1);
                 dD = 1.0f;                                             // :190 sentinel (Q6)
                 atten = 1.0f; total_v = 0.0f; onB = false; phi_n = 0.0f; steps = 0;   // :188-195
+                if (DELTA) alpha_x = alpha_at(a.F, x, y);
                 active = true;
             }
             const unsigned long long cnt = (unsigned long long)__popc(need);
@@ -139,7 +141,8 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
         const bool stepping = active && steps < a.max_steps && dD > a.eps;
         if (active && !stepping) {
             // terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7)
-            float bc = a.F.g.present ? field_eval(a.F.g, x, y) : 0.0f;
+            float bc = 0.0f;
+            if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, x, y) : field_eval_inl(a.F.g, x, y);
             if (DELTA) bc = bc * atten;
             a.walk_vals[id] = total_v + bc;
             if (TRACE) { if ((long long)id < a.n_trace) a.trace_len[id] = min(steps, a.trace_cap); }
@@ -239,7 +242,8 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
                 }
             }
 
-            float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f;
+            float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f, alpha_s = 1.0f;
+            bool have_alpha_s = false;
             if (DELTA) {
                 sbgn = interior_probability(r * a.sqrt_sigma_bar);                      // sigma_bar * |G^sb|(r)
                 gn = sbgn * a.inv_sigma_bar;                                            // screenedGreensNorm2D (utils.py:29-44)
@@ -261,22 +265,26 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkArgs a) {
                 if (norm2(sx - x, sy - y) > norm2(qx - x, qy - y)) {                    // :248-250
                     sx = qx; sy = qy;
                 } else if (SRC) {
-                    if (DELTA)                                                          // :252-254
-                        contrib = (field_eval(a.F.f, sx, sy) * gn / sqrtf(alpha_at(a.F, sx, sy) * alpha_at(a.F, x, y))) * atten;
-                    else
-                        contrib = field_eval(a.F.f, sx, sy) * (r * r / 4.0f);           // :256
+                    if (DELTA) {                                                        // :252-254
+                        alpha_s = alpha_at(a.F, sx, sy); have_alpha_s = true;
+                        contrib = (field_eval(a.F.f, sx, sy) * gn / sqrtf(alpha_s * alpha_x)) * atten;
+                    } else
+                        contrib = field_eval_inl(a.F.f, sx, sy) * (r * r / 4.0f);       // :256
                 }
                 if (SRC) total_v += contrib;                                            // :258
             }
             if (DELTA) {                                                                // :271-284
+                // alpha(current_point) is the value computed when the walker arrived here (same function, same point)
                 if (u24(o[1]) > sbgn) {
-                    atten = atten * sqrtf(alpha_at(a.F, qx, qy) / alpha_at(a.F, x, y));
-                    x = qx; y = qy;
+                    const float alpha_q = alpha_at(a.F, qx, qy);
+                    atten = atten * sqrtf(alpha_q / alpha_x);
+                    x = qx; y = qy; alpha_x = alpha_q;
                 } else {
+                    if (!have_alpha_s) alpha_s = alpha_at(a.F, sx, sy);
                     const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy);
                     const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);
-                    atten = (atten * sqrtf(alpha_at(a.F, sx, sy) / alpha_at(a.F, x, y))) * sc;
-                    x = sx; y = sy;
+                    atten = (atten * sqrtf(alpha_s / alpha_x)) * sc;
+                    x = sx; y = sy; alpha_x = alpha_s;
                 }
             } else { x = qx; y = qy; }                                                  // :287
             ++steps;                                                                    // :291
@@ -723,7 +731,7 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     const bool trace = n_trace > 0;
     const bool neu = scene->n_nseg > 0, src = fields && fields->f;
 
-    Staged<float> s_pts, s_vals, s_trace, s_icdf; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
+    Staged<float> s_pts, s_trace, s_icdf; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
     int rc;
     if ((rc = s_pts.init(pts_xy, 2 * n_pts, false, st))) return rc;
     if ((rc = s_icdf.init(delta ? P->screened_icdf : nullptr, delta ? P->icdf_len : 0, false, st))) return rc;
