@@ -6,7 +6,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -37,6 +39,10 @@ struct wost_scene {
     int sm_count = 0;
     size_t smem_optin = 0;
     float ndisc_x = 0.f, ndisc_y = 0.f, ndisc_r = 0.f, ndisc_r2 = 0.f;   // inflated disc enclosing the Neumann polyline
+    float4* dbvh = nullptr; int dbvh_leaves = 0;      // implicit BVH over the Dirichlet segments (large polylines only)
+    float4* nbvh = nullptr; int nbvh_leaves = 0;      // same for the Neumann segments
+    float4* ncones = nullptr;                          // silhouette cones of the Neumann hierarchy
+    float bvh_slack = 0.f;                             // ray/box slack (1e-4 of the scene scale)
 };
 
 struct wost_field {
@@ -65,6 +71,7 @@ struct WalkArgs {
     int chunk;                             // walks a warp reserves per atomic
     float ndisc_x, ndisc_y, ndisc_r, ndisc_r2;   // disc enclosing the Neumann polyline (inflated), for culling
     int sil_coop_max, ray_coop_max;        // answer a query cooperatively when at most this many lanes need it
+    Bvh dbvh, nbvh; float bvh_slack;       // hierarchies for large polylines (nodes == nullptr: brute force)
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
 
@@ -154,7 +161,8 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         float dN = CUDART_INF_F, r = 0.f, dx = 0.f, dy = 0.f, ex = 0.f, ey = 0.f, ox = 0.f, oy = 0.f;
         bool want_ray = false, want_sil = false;
         if (stepping) {
-            dD = dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);                     // :208
+            dD = a.dbvh.nodes ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, nullptr)
+                              : dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);      // :208
             uint32_t w0;
             if (!SRC && !DELTA) {
                 // Laplace walks use one 32-bit word per step: one Philox block (stream tag 1) serves four steps
@@ -190,7 +198,10 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             const bool small = a.n_nseg <= 32;                                          // warp-uniform
             float dN2 = CUDART_INF_F;                                                   // squared; rooted once below
             unsigned need = __ballot_sync(FULL, want_sil);                              // silhouette distance (:211)
-            if (__popc(need) > a.sil_coop_max) {
+            if (a.nbvh.nodes) {
+                // large polyline: per-lane descent; only vertices closer than dDirichlet can change r (:212)
+                if (want_sil) dN2 = bvh_silhouette_distance_sq(a.nseg, a.n_nseg, a.nbvh, x, y, TRACE ? CUDART_INF_F : dD * dD * 1.000001f);
+            } else if (__popc(need) > a.sil_coop_max) {
                 if (want_sil) dN2 = silhouette_distance_sq(nseg, a.n_nseg, x, y);
             } else {
                 while (need) {
@@ -203,7 +214,9 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             }
             dN = sqrtf(dN2);
             need = __ballot_sync(FULL, want_ray);                                       // ray vs polyline (:162-178)
-            if (__popc(need) > a.ray_coop_max) {
+            if (a.nbvh.nodes) {
+                if (want_ray) bvh_ray_cast(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, ox, oy, ex, ey, best_s, best_k);
+            } else if (__popc(need) > a.ray_coop_max) {
                 if (want_ray) ray_cast(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
             } else {
                 while (need) {
@@ -342,10 +355,11 @@ __global__ void merge_stats_kernel(const double* __restrict__ stats, long long n
 // =================================================================================================
 // kernels: batched primitives (parity entry points) — the same device functions the walk calls
 // =================================================================================================
-__global__ void geom_distance_kernel(const float4* seg, int n, const float* p, long long B, float* out_d, int* out_seg) {
+__global__ void geom_distance_kernel(const float4* seg, int n, Bvh bvh, const float* p, long long B, float* out_d, int* out_seg) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
-    int arg; const float d = dirichlet_distance(seg, n, p[2 * i], p[2 * i + 1], &arg);
+    int arg;
+    const float d = bvh.nodes ? bvh_dirichlet_distance(seg, n, bvh, p[2 * i], p[2 * i + 1], &arg) : dirichlet_distance(seg, n, p[2 * i], p[2 * i + 1], &arg);
     if (out_d) out_d[i] = d;
     if (out_seg) out_seg[i] = arg;
 }
@@ -358,10 +372,14 @@ __device__ __forceinline__ float4 seg_au(const SegView& s, int k) {
     return make_float4(a.x, a.y, u.x, u.y);
 }
 
-__global__ void geom_silhouette_kernel(SegView sv, const float* p, long long B, float* out_d, uint8_t* out_mask) {
+__global__ void geom_silhouette_kernel(SegView sv, Bvh bvh, const float* p, long long B, float* out_d, uint8_t* out_mask) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const float px = p[2 * i], py = p[2 * i + 1];
+    if (bvh.nodes && !out_mask && !sv.dirichlet_layout) {                // distance only: through the hierarchy
+        if (out_d) out_d[i] = sqrtf(bvh_silhouette_distance_sq(sv.seg, sv.n, bvh, px, py, CUDART_INF_F));
+        return;
+    }
     float sil = CUDART_INF_F, prev_c = 0.0f;
     for (int k = 0; k < sv.n; ++k) {
         const float4 s0 = seg_au(sv, k);
@@ -386,7 +404,7 @@ __global__ void geom_ray_kernel(SegView sv, const float* p, const float* dir, lo
     }
 }
 
-__global__ void geom_intersect_kernel(const float4* nseg, int n, const float* p, const float* dir, const float* rr, long long B,
+__global__ void geom_intersect_kernel(const float4* nseg, int n, Bvh bvh, float slack, const float* p, const float* dir, const float* rr, long long B,
                                       float* out_pt, float* out_nrm, uint8_t* out_found, int* out_seg) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
@@ -398,7 +416,8 @@ __global__ void geom_intersect_kernel(const float4* nseg, int n, const float* p,
         const float ex = dx / dn, ey = dy / dn;
         const float ox = x + 1e-6f * ex, oy = y + 1e-6f * ey;
         float best_s; int best_k;
-        ray_cast(nseg, n, ox, oy, ex, ey, best_s, best_k);
+        if (bvh.nodes) bvh_ray_cast(nseg, n, bvh, slack, ox, oy, ex, ey, best_s, best_k);
+        else ray_cast(nseg, n, ox, oy, ex, ey, best_s, best_k);
         if (best_k < 0 || best_s > r || best_s <= 0.0f) { qx = x + r * ex; qy = y + r * ey; nx = ny = 0.0f; }
         else {
             qx = ox + best_s * ex; qy = oy + best_s * ey;
@@ -498,6 +517,81 @@ static void tune_pool(int device) {
     });
 }
 
+// Implicit BVH over the index order of a polyline (see wost_device.cuh).  `xy` are the nvtx vertices.
+static std::vector<float4> build_bvh(const float* xy, int nvtx, float inflate, int* n_leaves_out) {
+    const int nseg = nvtx - 1;
+    int leaves = 1;
+    while (leaves * WOST_BVH_LEAF < nseg) leaves *= 2;
+    const float4 empty = make_float4(3e18f, 3e18f, 3e18f, 3e18f);       // a far-away point: never near, never hit
+    std::vector<float4> nodes(2 * (size_t)leaves, empty);
+    for (int j = 0; j < leaves; ++j) {
+        const int s0 = j * WOST_BVH_LEAF, s1 = std::min(s0 + WOST_BVH_LEAF, nseg);
+        if (s0 >= nseg) continue;
+        float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
+        for (int v = s0; v <= s1; ++v) {                                 // segments s0..s1-1 touch vertices s0..s1
+            xmin = std::fmin(xmin, xy[2 * v]); xmax = std::fmax(xmax, xy[2 * v]);
+            ymin = std::fmin(ymin, xy[2 * v + 1]); ymax = std::fmax(ymax, xy[2 * v + 1]);
+        }
+        nodes[leaves + j] = make_float4(xmin - inflate, ymin - inflate, xmax + inflate, ymax + inflate);
+    }
+    for (int i = leaves - 1; i >= 1; --i) {
+        const float4 a = nodes[2 * i], b = nodes[2 * i + 1];
+        const bool ea = a.x > a.z, eb = b.x > b.z;                       // never true for real boxes; empties are points
+        const bool a_empty = a.x == 3e18f, b_empty = b.x == 3e18f;
+        (void)ea; (void)eb;
+        if (a_empty && b_empty) nodes[i] = empty;
+        else if (b_empty) nodes[i] = a;
+        else if (a_empty) nodes[i] = b;
+        else nodes[i] = make_float4(std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmax(a.z, b.z), std::fmax(a.w, b.w));
+    }
+    *n_leaves_out = leaves;
+    return nodes;
+}
+
+// Direction cones for the silhouette cull (see cone_excludes_silhouette): per node (axis x, axis y, sin h, R).
+// Leaf j answers for vertices j*LEAF .. (j+1)*LEAF-1, whose tests involve segments j*LEAF-1 .. (j+1)*LEAF-1.
+static std::vector<float4> build_cones(const float* xy, int nvtx, const std::vector<float4>& nodes, int leaves) {
+    const int nseg = nvtx - 1;
+    struct Cone { double ax, ay, h; bool empty; };
+    std::vector<Cone> c(2 * (size_t)leaves, Cone{1.0, 0.0, 0.0, true});
+    auto merge = [](const Cone& a, const Cone& b) {
+        if (a.empty) return b;
+        if (b.empty) return a;
+        double sx = a.ax + b.ax, sy = a.ay + b.ay, n = std::sqrt(sx * sx + sy * sy);
+        Cone r{1.0, 0.0, M_PI, false};
+        if (n < 1e-9) return r;                                          // opposite axes: everything
+        r.ax = sx / n; r.ay = sy / n;
+        const double da = std::acos(std::fmax(-1.0, std::fmin(1.0, r.ax * a.ax + r.ay * a.ay)));
+        const double db = std::acos(std::fmax(-1.0, std::fmin(1.0, r.ax * b.ax + r.ay * b.ay)));
+        r.h = std::fmin(M_PI, std::fmax(da + a.h, db + b.h));
+        return r;
+    };
+    for (int j = 0; j < leaves; ++j) {
+        const int s0 = std::max(j * WOST_BVH_LEAF - 1, 0), s1 = std::min((j + 1) * WOST_BVH_LEAF, nseg);   // segments [s0, s1)
+        Cone acc{1.0, 0.0, 0.0, true};
+        for (int k = s0; k < s1; ++k) {
+            const double ux = (double)xy[2 * k + 2] - xy[2 * k], uy = (double)xy[2 * k + 3] - xy[2 * k + 1], n = std::sqrt(ux * ux + uy * uy);
+            acc = merge(acc, Cone{ux / n, uy / n, 0.0, false});
+        }
+        c[leaves + j] = acc;
+    }
+    for (int i = leaves - 1; i >= 1; --i) c[i] = merge(c[2 * i], c[2 * i + 1]);
+    std::vector<float4> out(2 * (size_t)leaves);
+    for (size_t i = 1; i < out.size(); ++i) {
+        const float4 b = nodes[i];
+        const double hx = 0.5 * ((double)b.z - b.x), hy = 0.5 * ((double)b.w - b.y);
+        const double R = std::sqrt(hx * hx + hy * hy) * 1.0001;          // boxes are already inflated
+        const bool usable = !c[i].empty && c[i].h < 0.5 * M_PI - 1e-3;
+        out[i] = make_float4((float)c[i].ax, (float)c[i].ay, usable ? (float)std::sin(c[i].h + 1e-4) : 2.0f, (float)R);
+    }
+    return out;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 typedef void (*walk_kernel_t)(const WalkArgs);
@@ -594,6 +688,31 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         const double R = std::sqrt(r2) * 1.001 + 1e-4 * scale + 1e-30;   // slack: fp32 rounding of s, t and of the cull itself
         s->ndisc_x = (float)cx; s->ndisc_y = (float)cy; s->ndisc_r = (float)R; s->ndisc_r2 = (float)(R * R);
     }
+    {   // hierarchies for large polylines (thresholds overridable for experiments)
+        double scale = 0.0;
+        for (int k = 0; k < 2 * nd; ++k) scale = std::fmax(scale, std::fabs((double)dxy[k]));
+        for (int k = 0; k < 2 * nn; ++k) scale = std::fmax(scale, std::fabs((double)nxy[k]));
+        const float inflate = (float)(1e-5 * scale + 1e-30);
+        s->bvh_slack = (float)(1e-4 * scale + 1e-30);
+        cudaError_t be = cudaSuccess;
+        if (s->n_dseg >= env_int("WOST_BVH_MIN_DIRICHLET", 48)) {
+            const std::vector<float4> nodes = build_bvh(dxy, nd, inflate, &s->dbvh_leaves);
+            be = cudaMalloc((void**)&s->dbvh, nodes.size() * sizeof(float4));
+            if (be == cudaSuccess) be = cudaMemcpy(s->dbvh, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice);
+        }
+        if (be == cudaSuccess && s->n_nseg >= env_int("WOST_BVH_MIN_NEUMANN", 192)) {
+            const std::vector<float4> nodes = build_bvh(nxy, nn, inflate, &s->nbvh_leaves);
+            be = cudaMalloc((void**)&s->nbvh, nodes.size() * sizeof(float4));
+            if (be == cudaSuccess) be = cudaMemcpy(s->nbvh, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice);
+            const std::vector<float4> cones = build_cones(nxy, nn, nodes, s->nbvh_leaves);
+            if (be == cudaSuccess) be = cudaMalloc((void**)&s->ncones, cones.size() * sizeof(float4));
+            if (be == cudaSuccess) be = cudaMemcpy(s->ncones, cones.data(), cones.size() * sizeof(float4), cudaMemcpyHostToDevice);
+        }
+        if (be != cudaSuccess) {
+            cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones); delete s;
+            return fail(WOST_ERR_CUDA, std::string("BVH upload: ") + cudaGetErrorString(be));
+        }
+    }
     tune_pool(device);
     *out = s;
     return WOST_OK;
@@ -602,7 +721,7 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
 int wost_scene_destroy(wost_scene_t* s) {
     if (!s) return WOST_OK;
     DeviceGuard g(s->device);
-    cudaFree(s->dseg); cudaFree(s->nseg);
+    cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones);
     delete s;
     return WOST_OK;
 }
@@ -775,6 +894,8 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
         if (a.sil_coop_max > 32) a.sil_coop_max = 32;
         if (a.ray_coop_max > 32) a.ray_coop_max = 32;
     }
+    a.dbvh.nodes = scene->dbvh; a.dbvh.n_leaves = scene->dbvh_leaves; a.nbvh.nodes = scene->nbvh; a.nbvh.cones = scene->ncones; a.nbvh.n_leaves = scene->nbvh_leaves;
+    a.bvh_slack = scene->bvh_slack;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;
@@ -872,7 +993,8 @@ int wost_geom_distance(const wost_scene_t* s, int32_t which, const float* p, int
     }
     Staged<float> sp, sd; Staged<int32_t> ss;
     if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sd.init(out_d, B, true, st)) || (rc = ss.init(out_seg, B, true, st))) return rc;
-    geom_distance_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, sp.dev, B, sd.dev, ss.dev);
+    Bvh bvh{}; if (v.dirichlet_layout) { bvh.nodes = s->dbvh; bvh.n_leaves = s->dbvh_leaves; }
+    geom_distance_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, bvh, sp.dev, B, sd.dev, ss.dev);
     CU(cudaGetLastError());
     const bool sync = sd.host_out() || ss.host_out();
     if ((rc = sp.finish()) || (rc = sd.finish()) || (rc = ss.finish())) return rc;
@@ -890,7 +1012,8 @@ int wost_geom_silhouette(const wost_scene_t* s, int32_t which, const float* p, i
     cudaStream_t st = (cudaStream_t)stream;
     Staged<float> sp, sd; Staged<uint8_t> sm;
     if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sd.init(out_d, B, true, st)) || (rc = sm.init(out_mask, (size_t)B * (v.n - 1), true, st))) return rc;
-    geom_silhouette_kernel<<<blocks_for(B, 256), 256, 0, st>>>(v, sp.dev, B, sd.dev, sm.dev);
+    Bvh bvh{}; if (!v.dirichlet_layout) { bvh.nodes = s->nbvh; bvh.cones = s->ncones; bvh.n_leaves = s->nbvh_leaves; }
+    geom_silhouette_kernel<<<blocks_for(B, 256), 256, 0, st>>>(v, bvh, sp.dev, B, sd.dev, sm.dev);
     CU(cudaGetLastError());
     const bool sync = sd.host_out() || sm.host_out();
     if ((rc = sp.finish()) || (rc = sd.finish()) || (rc = sm.finish())) return rc;
@@ -944,7 +1067,8 @@ int wost_geom_intersect(const wost_scene_t* s, int32_t which, const float* p, co
     if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sdir.init(dir, 2 * B, false, st)) || (rc = sr.init(r, B, false, st)) ||
         (rc = spt.init(out_pt, 2 * B, true, st)) || (rc = snr.init(out_nrm, 2 * B, true, st)) || (rc = sf.init(out_found, B, true, st)) ||
         (rc = ss.init(out_seg, B, true, st))) return rc;
-    geom_intersect_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, sp.dev, sdir.dev, sr.dev, B, spt.dev, snr.dev, sf.dev, ss.dev);
+    Bvh bvh{}; if (!v.dirichlet_layout) { bvh.nodes = s->nbvh; bvh.n_leaves = s->nbvh_leaves; }
+    geom_intersect_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, bvh, s->bvh_slack, sp.dev, sdir.dev, sr.dev, B, spt.dev, snr.dev, sf.dev, ss.dev);
     CU(cudaGetLastError());
     const bool sync = spt.host_out() || snr.host_out() || sf.host_out() || ss.host_out();
     if ((rc = sp.finish()) || (rc = sdir.finish()) || (rc = sr.finish()) || (rc = spt.finish()) || (rc = snr.finish()) || (rc = sf.finish()) || (rc = ss.finish())) return rc;

@@ -336,3 +336,58 @@ def test_device_pointer_path_matches_host_path():
     dev = solver.solve_raw(s.points.cuda(), 512, s.max_steps, s.eps, seed=9, device_outputs=True)
     torch.cuda.synchronize()
     assert np.array_equal(dev["mean"].cpu().numpy(), host["mean"]) and int(dev["steps"][0]) == int(host["steps"][0])
+
+
+# ---- large polylines: the implicit BVH must not change a single bit -------------------------------------
+def test_bvh_walks_bit_identical_to_brute_force(monkeypatch):
+    s = sc.scale_scene(1024, n_points=512, n_walks=32)
+    with_bvh = s.make_solver().solve_raw(s.points, 32, s.max_steps, s.eps, seed=4, want_walk_vals=True, n_trace=64, trace_cap=16)
+    monkeypatch.setenv("WOST_BVH_MIN_DIRICHLET", "100000000")
+    monkeypatch.setenv("WOST_BVH_MIN_NEUMANN", "100000000")
+    brute = s.make_solver().solve_raw(s.points, 32, s.max_steps, s.eps, seed=4, want_walk_vals=True, n_trace=64, trace_cap=16)
+    assert np.array_equal(bits(with_bvh["walk_vals"]), bits(brute["walk_vals"]))
+    assert int(with_bvh["steps"][0]) == int(brute["steps"][0])
+    assert np.array_equal(with_bvh["trace_len"], brute["trace_len"])
+    assert np.array_equal(bits(np.nan_to_num(with_bvh["trace"], nan=-1.0)), bits(np.nan_to_num(brute["trace"], nan=-1.0)))
+    # and against the (brute-force) oracle on the same Philox stream
+    o = orc.Problem.from_scenario(s).solve(s.points[:64], 32, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=4, walk_vals=True)
+    dv = np.abs(with_bvh["walk_vals"][:64] - o["walk_vals"])
+    assert (dv <= 2e-3 * (1 + np.abs(o["walk_vals"]))).mean() > 0.9
+
+
+@pytest.mark.parametrize("shape", ["ngon", "topography", "spiral"])
+def test_bvh_primitives_bit_identical_on_awkward_polylines(shape, monkeypatch):
+    g = torch.Generator().manual_seed(17)
+    if shape == "ngon":
+        pts = sc.ngon(1.0, 2000)
+    elif shape == "topography":                                            # open heightmap polyline (funcToPolyline style)
+        x = torch.arange(0, 60.0, 0.02)
+        pts = torch.stack((x, 2.0 * torch.sin(0.3 * x) + 0.3 * torch.sin(3.1 * x)), dim=-1)
+    else:                                                                  # self-approaching spiral with uneven segment lengths
+        t = torch.linspace(0.2, 25.0, 1500) ** 1.3
+        pts = torch.stack((0.05 * t * torch.cos(t), 0.05 * t * torch.sin(t)), dim=-1).to(torch.float32)
+    lo, hi = pts.min(0).values, pts.max(0).values
+    q = lo + (hi - lo) * (torch.rand(2500, 2, generator=g) * 1.2 - 0.1)
+    k = torch.randint(0, len(pts) - 1, (2500,), generator=g)
+    q[::4] = (pts[k] * 0.5 + pts[k + 1] * 0.5)[::4]                          # queries on the polyline
+    th = torch.rand(2500, generator=g) * 6.2831853
+    d = torch.stack([torch.cos(th), torch.sin(th)], 1)
+    d[::50] = torch.tensor([1.0, 0.0]); d[25::50] = torch.tensor([0.0, -1.0])   # axis-parallel rays
+    r = torch.rand(2500, generator=g) * float((hi - lo).max()) * 0.5 + 1e-3
+    poly = PolyLinesSimple(pts)
+    out_bvh = (poly.distance(q), poly.silhouetteDistance(q), *poly.intersectPolylines(q, d, r), poly.last_hit_segment)
+    monkeypatch.setenv("WOST_BVH_MIN_DIRICHLET", "100000000")
+    monkeypatch.setenv("WOST_BVH_MIN_NEUMANN", "100000000")
+    brute = PolyLinesSimple(pts.clone() + 0.0)
+    brute._scene = None
+    import dcrmontecarlo_b200._native as n2
+    brute._scene, brute._scene_key = n2.Scene(pts, pts), (n2.host_f32(pts).tobytes(), n2.current_device())
+    out_brute = (brute.distance(q), brute.silhouetteDistance(q), *brute.intersectPolylines(q, d, r), brute.last_hit_segment)
+    for a, b in zip(out_bvh, out_brute):
+        if a.dtype == torch.float32:
+            assert np.array_equal(bits(a), bits(b))
+        else:
+            assert torch.equal(a, b)
+    assert np.array_equal(bits(out_bvh[0]), bits(orc.distance(pts, q)))
+    assert np.array_equal(bits(out_bvh[1]), bits(orc.silhouette_distance(pts, q)))
+    assert out_bvh[4].sum() > 50                                           # the test does exercise hits
