@@ -219,25 +219,27 @@ class GridField(Field):
         ys = torch.linspace(ymin - my, ymax + my, n)
         X, Y = torch.meshgrid(xs, ys, indexing="ij")
         vals = None
+        # no torch.no_grad() here: callables may differentiate internally (the solver's sigma' does)
         try:
-            with torch.no_grad():
-                out = fn(torch.stack([X.flatten(), Y.flatten()], dim=0))
-            out = torch.as_tensor(out, dtype=torch.float32)
+            out = fn(torch.stack([X.flatten(), Y.flatten()], dim=0))
+            out = torch.as_tensor(out, dtype=torch.float32).detach()
             if out.shape == (n * n,):
                 probe = [0, n * n // 3, n * n // 2 + 7, n * n - 1]
-                ok = all(
-                    abs(float(fn(torch.stack([X.flatten()[i], Y.flatten()[i]]))) - float(out[i])) <= 1e-5 * (1.0 + abs(float(out[i])))
-                    for i in probe
-                )
+                def one(i):
+                    v = fn(torch.stack([X.flatten()[i], Y.flatten()[i]]))
+                    return float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
+
+                ok = all(abs(one(i) - float(out[i])) <= 1e-5 * (1.0 + abs(float(out[i]))) for i in probe)
                 if ok:
                     vals = out.reshape(n, n)
         except Exception:
             vals = None
         if vals is None:
             flat = torch.empty(n * n, dtype=torch.float32)
-            with torch.no_grad():
-                for i in range(n * n):
-                    flat[i] = float(fn(torch.stack([X.flatten()[i], Y.flatten()[i]])))
+            xf, yf = X.flatten(), Y.flatten()
+            for i in range(n * n):
+                v = fn(torch.stack([xf[i], yf[i]]))
+                flat[i] = float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
             vals = flat.reshape(n, n)
         return GridField(vals.numpy(), float(xs[0]), float(ys[0]), float(xs[1] - xs[0]), float(ys[1] - ys[0]))
 
@@ -259,8 +261,9 @@ class GridField(Field):
                     x0=self.x0, y0=self.y0, dx=self.dx, dy=self.dy)
 
 
-def as_field(obj, bounds=None, n: int = 257) -> Field | None:
-    """``None`` stays ``None``; numbers become constants; Field passes through; any other callable is tabulated."""
+def as_field(obj, bounds=None, n: int = 257, trace: bool = True) -> Field | None:
+    """``None`` stays ``None``; numbers become constants; Field passes through; any other callable is first traced
+    symbolically into an exact :class:`TermField` (:mod:`fieldtrace`) and, if that is not possible, tabulated."""
     if obj is None or isinstance(obj, Field):
         return obj
     if isinstance(obj, (int, float)):
@@ -268,6 +271,15 @@ def as_field(obj, bounds=None, n: int = 257) -> Field | None:
     if callable(obj):
         if bounds is None:
             raise ValueError("tabulating a callable needs domain bounds")
+        if trace:
+            try:
+                from .fieldtrace import trace_callable
+            except ImportError:  # reference-style sys.path layout
+                from fieldtrace import trace_callable
+
+            exact = trace_callable(obj, bounds)
+            if exact is not None:
+                return exact
         return GridField.from_callable(obj, bounds, n=n)
     raise TypeError(f"cannot turn {type(obj)} into a field")
 

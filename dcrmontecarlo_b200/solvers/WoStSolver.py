@@ -127,7 +127,8 @@ class WostSolver_2D:
         if (sigma_bar <= 0) | (sigma_bar > 1e3):                         # :134-136
             sigma_bar = 10.0
         # which device formulation reproduces this closure
-        analytic = all(isinstance(c, TermField) or not given
+        # (plain callables that are closed-form expressions are traced into exact TermFields, see fieldtrace.py)
+        analytic = all(not given or isinstance(self._host_field(c), TermField)
                        for c, given in ((self.alpha, self._alpha_given), (self.sigma, self._sigma_given)))
         if self._autograd_failed or self.sigma_prime_mode == "ratio":
             self.sp_mode = SP_RATIO

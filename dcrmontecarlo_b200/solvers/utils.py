@@ -102,3 +102,45 @@ class ScreenedGreensDistribution2D(SamplingDistribution2D):
         if r <= 0 or r >= radius:
             return 0.0
         return abs(screenedGreens2D(torch.zeros(2), torch.tensor([r, 0.0]), radius, self.sigma_bar)) / screenedGreensNorm2D(radius, self.sigma_bar)
+
+
+# ---- multiple-importance-sampling helpers ----------------------------------------------------------------
+# The reference ships these (solvers/utils.py:198-324) but neither its solver nor its tests call them; they are kept
+# importable, host-side only, so code written against the reference's module keeps working.
+class UniformDistribution2D(SamplingDistribution2D):
+    """Radius uniform on [0, radius] (reference :198-217)."""
+
+    def sample(self, center, radius):
+        return np.random.uniform(0, radius)
+
+    def pdf(self, r, center, radius):
+        return 1.0 / radius if 0 <= r <= radius else 0.0
+
+
+class MultipleImportanceSampler2D:
+    """Mixture of radius distributions with balance-heuristic weights (reference :220-286)."""
+
+    def __init__(self, distributions: list, weights: list = None):
+        self.distributions = distributions
+        w = np.asarray(weights if weights else [1.0] * len(distributions), dtype=float)
+        self.weights = w / w.sum()
+
+    def sample(self, center, radius):
+        i = int(np.random.choice(len(self.distributions), p=self.weights))
+        r = self.distributions[i].sample(center, radius)
+        return r, i, self._compute_mis_weight(r, center, radius, i)
+
+    def _compute_mis_weight(self, r, center, radius, sampled_idx):
+        wp = self.weights * np.array([d.pdf(r, center, radius) for d in self.distributions])
+        tot = wp.sum()
+        return 0.0 if tot == 0 else float(wp[sampled_idx] / tot)
+
+
+def sampleGreensFunction2D(center, radius, distribution: SamplingDistribution2D = None) -> float:
+    """One Green's-function radius (reference :289-304)."""
+    return (distribution or GreensDistribution2D()).sample(center, radius)
+
+
+def sampleScreenedGreensFunction2D(center, radius, sigma_bar, distribution: "ScreenedGreensDistribution2D" = None) -> float:
+    """One screened-Green's-function radius (reference :307-324)."""
+    return (distribution or ScreenedGreensDistribution2D(sigma_bar)).sample(center, radius)

@@ -1,0 +1,109 @@
+"""DC-resistivity survey driver: many current-electrode pairs over one line of measurement electrodes.
+
+The reference solves one source pair at a time by editing a script (``tests/testGeophysicalScenario.py:11-33,109-151``;
+the notebook variant ``tests/testNotebook.ipynb`` cells 3, 17-21 builds a dipole-dipole line and differences
+``V_M - V_N`` between neighbouring electrodes).  Here a survey is a list of source dipoles sharing the geometry and the
+conductivity field; each source is one launch of the walk kernel over all measurement electrodes, and sources are
+sharded over GPUs (``torch.distributed``) when a process group is initialised.
+
+Current electrodes are Gaussian blobs like the reference's (``norm = I / (2 pi w^2)``, ``exp(-d^2 / (2 w^2))``).
+``sink_sign=-1`` gives a physical dipole (+I at A, -I at B, as in the notebook); ``sink_sign=+1`` reproduces
+``testGeophysicalScenario.py:29-33``, where the "sink" enters with a positive sign.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from .fields import Field, TermField
+from .geometry.Polylines import PolyLines
+from .solvers.WoStSolver import WostSolver_2D
+
+
+@dataclass(frozen=True)
+class DipoleSource:
+    a: tuple            # (x, y) of the +I electrode
+    b: tuple            # (x, y) of the -I electrode
+    current: float = 1.0
+    width: float = 0.5  # Gaussian width of the injection (reference: sigma = 0.5 m)
+
+    def field(self, sink_sign: float = -1.0) -> TermField:
+        norm = self.current / (2.0 * math.pi * self.width ** 2)
+        q = 1.0 / (2.0 * self.width ** 2)
+        return TermField.gaussian_sum([(norm, tuple(map(float, self.a)), q), (sink_sign * norm, tuple(map(float, self.b)), q)])
+
+
+def geometric_factor_2d(a, b, m, n) -> float:
+    """Geometric factor K of a four-electrode array on a homogeneous 2D half-plane (line electrodes):
+    V(r) = -(rho I / pi) ln r  =>  rho_a = K * (V_M - V_N) / I  with  K = pi / (ln(BM/AM) - ln(BN/AN))."""
+    d = lambda p, q: math.hypot(p[0] - q[0], p[1] - q[1])                # noqa: E731
+    dists = (d(a, m), d(b, m), d(a, n), d(b, n))
+    if min(dists) == 0.0:                                                # a potential electrode sits on a current electrode
+        return float("nan")
+    den = math.log(dists[1] / dists[0]) - math.log(dists[3] / dists[2])
+    return math.pi / den if den != 0.0 else float("nan")
+
+
+class DCRSurvey:
+    def __init__(self, dirichletBoundary: PolyLines, neumannBoundary: PolyLines, conductivity: Field,
+                 electrodes: torch.Tensor, sources: Sequence[DipoleSource], receivers: Sequence[tuple] | None = None,
+                 sink_sign: float = -1.0):
+        self.electrodes = torch.as_tensor(electrodes, dtype=torch.float32).reshape(-1, 2).contiguous()
+        self.sources = list(sources)
+        E = self.electrodes.shape[0]
+        # receiver dipoles (M, N) as electrode indices; default: neighbouring electrodes (notebook cell 3)
+        self.receivers = [(i, i + 1) for i in range(E - 1)] if receivers is None else [tuple(r) for r in receivers]
+        self.sink_sign = float(sink_sign)
+        # one solver: sigma' and sigma_bar depend on the conductivity only (no absorption in DC resistivity)
+        self.solver = WostSolver_2D(dirichletBoundary, None, neumannBoundary, source=None, sigma=None, alpha=conductivity)
+        self._fields = [s.field(self.sink_sign) for s in self.sources]
+
+    def run(self, nWalks: int = 1000, maxSteps: int = 500, eps: float = 0.9, seed: int | None = None) -> dict:
+        """Potentials at every electrode for every source.  Returns
+        ``potentials`` (S, E) float64, ``stderr`` (S, E), ``dV`` (S, R) = V_M - V_N per receiver dipole, ``steps``.
+        With an initialised ``torch.distributed`` group the sources are dealt round-robin to the ranks and the
+        result is gathered on every rank; the same ``seed`` gives the same numbers for any number of ranks."""
+        import torch.distributed as dist
+
+        world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
+        if seed is None:
+            hi, lo = torch.randint(0, 1 << 31, (2,), dtype=torch.int64).tolist()
+            seed = (hi << 31) | lo
+        if world > 1:                                                     # one key for the whole job
+            t = torch.tensor([seed if rank == 0 else 0], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            dist.broadcast(t, src=0)
+            seed = int(t.item())
+        S, E = len(self.sources), self.electrodes.shape[0]
+        pot, m2 = np.zeros((S, E)), np.zeros((S, E))
+        steps = 0
+        for s in range(rank, S, world):
+            self.solver.setSourceTerm(self._fields[s])
+            # the source index goes into the Philox key, so every source walks its own paths
+            r = self.solver.solve_raw(self.electrodes, nWalks, maxSteps, eps, seed=(seed + 0x9E3779B97F4A7C15 * (s + 1)) % (1 << 64))
+            pot[s], m2[s] = r["mean"], r["m2"]
+            steps += int(r["steps"][0])
+        if world > 1:
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            buf = torch.from_numpy(np.stack([pot, m2])).to(dev)
+            dist.all_reduce(buf)                                          # disjoint rows: the sum is a gather
+            st = torch.tensor([steps], dtype=torch.int64, device=dev)
+            dist.all_reduce(st)
+            pot, m2, steps = buf[0].cpu().numpy(), buf[1].cpu().numpy(), int(st.item())
+        n = float(nWalks)
+        stderr = np.sqrt(m2 / max(n - 1.0, 1.0) / n)
+        M = np.array([r[0] for r in self.receivers]); N = np.array([r[1] for r in self.receivers])
+        return dict(potentials=pot, stderr=stderr, dV=pot[:, M] - pot[:, N], dV_stderr=np.hypot(stderr[:, M], stderr[:, N]),
+                    steps=steps, seed=seed)
+
+    def apparent_resistivity(self, dV: np.ndarray) -> np.ndarray:
+        """rho_a (S, R) from the receiver voltages with the 2D half-plane geometric factor of each (A, B, M, N)."""
+        out = np.zeros_like(dV)
+        el = self.electrodes.numpy()
+        for s, src in enumerate(self.sources):
+            for k, (m, n) in enumerate(self.receivers):
+                out[s, k] = geometric_factor_2d(src.a, src.b, el[m], el[n]) * dV[s, k] / src.current
+        return out

@@ -391,3 +391,101 @@ def test_bvh_primitives_bit_identical_on_awkward_polylines(shape, monkeypatch):
     assert np.array_equal(bits(out_bvh[0]), bits(orc.distance(pts, q)))
     assert np.array_equal(bits(out_bvh[1]), bits(orc.silhouette_distance(pts, q)))
     assert out_bvh[4].sum() > 50                                           # the test does exercise hits
+
+
+# ---- DCR survey driver --------------------------------------------------------------------------------------
+def test_dcr_survey_driver():
+    from dcrmontecarlo_b200.survey import DCRSurvey, DipoleSource
+
+    s = sc.cfg5(9)
+    srcs = [DipoleSource((-10.0, 0.0), (10.0, 0.0)), DipoleSource((10.0, 0.0), (-10.0, 0.0)), DipoleSource((-30.0, 0.0), (20.0, 0.0))]
+    survey = DCRSurvey(PolyLinesSimple(s.dirichlet), PolyLinesSimple(s.neumann), s.alpha, s.points, srcs)
+    assert survey.solver.sigma_bar == 10.0
+    out = survey.run(nWalks=4096, maxSteps=s.max_steps, eps=s.eps, seed=5)
+    assert out["potentials"].shape == (3, 9) and out["dV"].shape == (3, 8) and out["steps"] > 0
+    assert np.allclose(out["dV"], out["potentials"][:, :-1] - out["potentials"][:, 1:])
+    # a source is exactly what the plain solver computes with that source term and key
+    direct = WostSolver_2D(PolyLinesSimple(s.dirichlet), None, PolyLinesSimple(s.neumann), source=srcs[2].field(), alpha=s.alpha)
+    r = direct.solve_raw(s.points, 4096, s.max_steps, s.eps, seed=(5 + 0x9E3779B97F4A7C15 * 3) % (1 << 64))
+    assert np.array_equal(r["mean"], out["potentials"][2])
+    # physics sanity: potential is positive next to the +I electrode and negative next to the -I electrode
+    x = s.points[:, 0].numpy()
+    assert out["potentials"][0][x == -10.0][0] > 0 > out["potentials"][0][x == 10.0][0]
+    rho = survey.apparent_resistivity(out["dV"])
+    assert rho.shape == (3, 8) and np.isfinite(rho).sum() >= 12        # nan where M or N coincides with A or B
+    # the reference script's sign quirk (both blobs positive) is available too
+    quirk = DCRSurvey(PolyLinesSimple(s.dirichlet), PolyLinesSimple(s.neumann), s.alpha, s.points, srcs[:1], sink_sign=+1.0)
+    ref_like = s.make_solver().solve_raw(s.points, 2048, s.max_steps, s.eps, seed=(9 + 0x9E3779B97F4A7C15) % (1 << 64))
+    assert np.array_equal(quirk.run(nWalks=2048, maxSteps=s.max_steps, eps=s.eps, seed=9)["potentials"][0], ref_like["mean"])
+
+
+# ---- drop-in usage: the reference's import style and plain callables ---------------------------------------------
+def test_dropin_module_layout_runs_reference_style_script(tmp_path):
+    """A user script written against the reference (sys.path -> repo root, `from solvers.WoStSolver import ...`,
+    plain callables as in tests/testWoStCorrectness.py) runs unchanged with dcrmontecarlo_b200/ on the path."""
+    import subprocess
+    import sys as _sys
+    from pathlib import Path
+
+    pkg = Path(nat.__file__).resolve().parent
+    script = tmp_path / "user_script.py"
+    script.write_text(f"""
+import sys
+sys.path.insert(0, {str(pkg)!r})
+import torch, numpy as np
+from solvers.WoStSolver import WostSolver_2D
+from geometry.PolylinesSimple import PolyLines, PolyLinesSimple
+from utils import torch_smooth_circle, gridSampleMinMax
+
+h = 1.0
+boundary = PolyLinesSimple(torch.tensor([[-h, -h], [h, -h], [h, h], [-h, h], [-h, -h]]))
+def diffusion_coefficient(point): return 2.0 + 0.5 * point[0] + 0.5 * point[1]
+def absorption_coefficient(point): return point[0] * point[1] + 2
+def boundary_condition(point):
+    x, y = point[0], point[1]
+    return (1 - x**2) * (1 - y**2)
+def source_term(point):
+    x, y = point[0], point[1]
+    u = (1 - x**2) * (1 - y**2)
+    D = 2 + 0.5*x + 0.5*y
+    return -(D * (-2 * (2 - x**2 - y**2)) + (-x*(1 - y**2) - y*(1 - x**2))) + (2 + x * y) * u
+x = torch.linspace(-0.7, 0.7, 4)
+X, Y = torch.meshgrid(x, x, indexing='ij')
+pts = torch.stack([X.flatten(), Y.flatten()], dim=1)
+torch.manual_seed(42); np.random.seed(42)
+solver = WostSolver_2D(dirichletBoundary=boundary, neumannBoundary=None, source=source_term, alpha=diffusion_coefficient, sigma=absorption_coefficient)
+solver.setBoundaryConditions(boundary_condition)
+solver.setSourceTerm(source_term)
+assert solver.use_delta_tracking and abs(solver.sigma_bar - 2.40625) < 1e-6
+sol = solver.solve(pts, nWalks=20000, maxSteps=800)
+exact = (1 - pts[:, 0]**2) * (1 - pts[:, 1]**2)
+print('RMSE', float(torch.sqrt(((sol.flatten() - exact)**2).mean())), tuple(sol.shape))
+""")
+    out = subprocess.run([_sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rmse = float(out.stdout.split("RMSE")[1].split()[0])
+    assert rmse < 0.04 and "(16, 1)" in out.stdout
+
+
+def test_tabulated_fields_and_sigma_prime_field_path_match_oracle():
+    """Coefficients outside the term algebra: alpha, sigma' are tabulated (GridField, WOST_SP_FIELD); same tables in the
+    oracle => same walks."""
+    s = sc.cfg1b()
+    alpha = lambda p: 2.0 + torch.sqrt(p[0] ** 2 + 1.0) * 0.5 + 0.25 * p[1]              # noqa: E731
+    solver = WostSolver_2D(PolyLinesSimple(s.dirichlet), s.g, None, source=s.f, alpha=alpha, sigma=s.sigma,
+                           field_resolution=129, sigma_prime_resolution=33)
+    assert solver.sp_mode == nat.SP_FIELD and solver.use_delta_tracking
+    a_grid = solver._host_field(solver.alpha)
+    sp_grid = solver._host_field(solver._sigma_prime_plain, solver.sigma_prime_resolution)
+    assert isinstance(a_grid, GridField) and isinstance(sp_grid, GridField)
+    pts, W = s.points[:8].contiguous(), 128
+    r = solver.solve_raw(pts, W, s.max_steps, s.eps, seed=17, want_walk_vals=True)
+    icdf = solver._cache[("icdf", float(solver.sigma_bar), nat.current_device())].cpu().numpy()
+    prob = orc.Problem(s.dirichlet, None, g=s.g, f=s.f, alpha=a_grid, sigma=s.sigma, sigma_prime=sp_grid, sigma_bar=solver.sigma_bar)
+    o = prob.solve(pts, W, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=17, icdf=icdf, walk_vals=True)
+    dv = np.abs(r["walk_vals"] - o["walk_vals"])
+    assert (dv <= 2e-3 * (1 + np.abs(o["walk_vals"]))).mean() > 0.9
+    assert np.all(np.abs(r["mean"] - o["mean"]) <= o["stderr"] + 1e-6)
+    # sigma' table vs the closed form of the true alpha
+    q = torch.tensor([0.3, -0.2])
+    assert float(sp_grid(q)) == pytest.approx(float(solver.sigma_prime(q)), rel=2e-2, abs=2e-3)

@@ -176,7 +176,9 @@ def test_solver_attributes_and_plain_callables():
     # alpha = 2 + x, sigma = 1 at (0.3, 0.2): closed form 0.3875236 (SURVEY §8c probe)
     sa = WostSolver_2D(PolyLinesSimple(s.dirichlet), alpha=lambda p: 2.0 + p[0], sigma=lambda p: 1.0 + 0.0 * p[0])
     assert float(sa.sigma_prime(torch.tensor([0.3, 0.2]))) == pytest.approx(0.3875236, abs=1e-6)
-    assert sa.sp_mode == nat.SP_FIELD
+    assert sa.sp_mode == nat.SP_FULL                 # closed-form callables are traced into exact device fields
+    su = WostSolver_2D(PolyLinesSimple(s.dirichlet), alpha=lambda p: 2.0 + torch.sqrt(p[0] ** 2 + 1.0), sigma=lambda p: 1.0 + 0.0 * p[0])
+    assert su.sp_mode == nat.SP_FIELD                # differentiable but outside the term algebra: sigma' is tabulated
     with pytest.raises(ValueError):
         WostSolver_2D(PolyLinesSimple(s.dirichlet), sigma_prime_mode="bogus")
 
@@ -209,3 +211,31 @@ def test_scenarios_match_survey_sizes():
     big = sc.cfg2_throughput(4096, 8)
     assert big.points.shape == (4096, 2) and float(torch.norm(big.points, dim=1).min()) > 0.6
     assert sc.scale_scene(64, 128, 4).dirichlet.shape == (65, 2)
+
+
+def test_mis_helpers_importable_and_consistent():
+    np.random.seed(3)
+    mis = SU.MultipleImportanceSampler2D([SU.GreensDistribution2D(), SU.UniformDistribution2D()], [3.0, 1.0])
+    assert np.allclose(mis.weights, [0.75, 0.25])
+    r, i, w = mis.sample(None, 2.0)
+    assert 0 < r <= 2.0 and i in (0, 1) and 0.0 <= w <= 1.0
+    tot = sum(mis._compute_mis_weight(0.7, None, 2.0, k) for k in range(2))
+    assert tot == pytest.approx(1.0)
+    assert 0 < SU.sampleGreensFunction2D(None, 1.0) <= 1.0 and 0 < SU.sampleScreenedGreensFunction2D(None, 1.0, 2.0) <= 1.0
+    assert SU.UniformDistribution2D().pdf(0.5, None, 2.0) == 0.5 and SU.UniformDistribution2D().pdf(3.0, None, 2.0) == 0.0
+
+
+def test_survey_helpers():
+    from dcrmontecarlo_b200.survey import DipoleSource, geometric_factor_2d
+
+    src = DipoleSource((-10.0, 0.0), (10.0, 0.0), current=2.0, width=0.5)
+    f = src.field()
+    nrm = 2.0 / (2 * np.pi * 0.25)
+    assert f(torch.tensor([-10.0, 0.0])).item() == pytest.approx(nrm, rel=1e-6)
+    assert f(torch.tensor([10.0, 0.0])).item() == pytest.approx(-nrm, rel=1e-6)
+    assert src.field(sink_sign=+1.0)(torch.tensor([10.0, 0.0])).item() == pytest.approx(nrm, rel=1e-6)   # reference quirk
+    # homogeneous half-plane: V = -(rho I/pi) ln r per electrode  =>  K dV / I recovers rho
+    a, b, m, n = (-3.0, 0.0), (3.0, 0.0), (-1.0, 0.0), (1.5, 0.0)
+    rho, I = 40.0, 1.0
+    V = lambda p: -(rho * I / np.pi) * (np.log(np.hypot(p[0] - a[0], p[1])) - np.log(np.hypot(p[0] - b[0], p[1])))   # noqa: E731
+    assert geometric_factor_2d(a, b, m, n) * (V(m) - V(n)) / I == pytest.approx(rho)
