@@ -18,6 +18,7 @@ LIB_PATH = Path(os.environ.get("WOST_LIB", PKG / "libwost.so"))   # WOST_LIB: al
 
 WALK_BLOCK = 1024
 SP_FULL, SP_RATIO, SP_FIELD = 0, 1, 2
+COMPAT = {"reference": 0, "physical": 1}
 
 
 class WostError(RuntimeError):
@@ -45,7 +46,8 @@ class Fields(C.Structure):
 class SolveParams(C.Structure):
     _fields_ = [("n_walks", C.c_int64), ("max_steps", C.c_int32), ("eps", C.c_float), ("delta_tracking", C.c_int32),
                 ("sp_mode", C.c_int32), ("sigma_bar", C.c_float), ("screened_icdf", C.c_void_p), ("icdf_len", C.c_int32),
-                ("seed", C.c_uint64), ("point_index_base", C.c_int64), ("walk_offset", C.c_int64), ("reserved", C.c_int32 * 4)]
+                ("seed", C.c_uint64), ("point_index_base", C.c_int64), ("walk_offset", C.c_int64), ("compat_mode", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 EXPORTS = {
@@ -189,7 +191,7 @@ def sigma_prime_eval(fields: Fields, sp_mode: int, pts, device: int):
 def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: float, *, delta: bool = False,
           sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0, point_index_base: int = 0,
           walk_offset: int = 0, want_block_stats: bool = False, want_walk_vals: bool = False, n_trace: int = 0,
-          trace_cap: int = 0, device_outputs: bool = False):
+          trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference"):
     """One wost_solve call.  ``pts`` may be a host array/tensor or a CUDA tensor on the scene's device.
     With ``device_outputs`` the results stay on the device as torch tensors (stream-ordered, no sync)."""
     dev = scene.device
@@ -207,6 +209,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
         icdf_keep = icdf if (isinstance(icdf, torch.Tensor) and icdf.is_cuda) else host_f32(icdf)
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
+    prm.compat_mode = COMPAT[compat]
 
     if device_outputs:
         tdev = torch.device("cuda", dev)

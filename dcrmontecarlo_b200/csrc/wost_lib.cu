@@ -43,6 +43,8 @@ struct wost_scene {
     float4* nbvh = nullptr; int nbvh_leaves = 0;      // same for the Neumann segments
     float4* ncones = nullptr;                          // silhouette cones of the Neumann hierarchy
     float bvh_slack = 0.f;                             // ray/box slack (1e-4 of the scene scale)
+    int neu_closed = 0;                                // first Neumann vertex == last
+    float phys_nudge = 0.f;                            // 1e-5 of the scene scale
 };
 
 struct wost_field {
@@ -72,6 +74,7 @@ struct WalkArgs {
     float ndisc_x, ndisc_y, ndisc_r, ndisc_r2;   // disc enclosing the Neumann polyline (inflated), for culling
     int sil_coop_max, ray_coop_max;        // answer a query cooperatively when at most this many lanes need it
     Bvh dbvh, nbvh; float bvh_slack;       // hierarchies for large polylines (nodes == nullptr: brute force)
+    int neu_closed; float phys_nudge;      // physical mode: closed Neumann loop?  pull-back of a reflected walker
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
 
@@ -81,7 +84,7 @@ struct WalkArgs {
 // consecutive walk indices per global atomic and deal them out with ballot/popc.
 //
 // The loop body restates solvers/WoStSolver.py:206-298 of the reference, quirks included.
-template <bool NEU, bool SRC, bool DELTA, bool TRACE>
+template <bool NEU, bool SRC, bool DELTA, bool TRACE, bool PHYS>
 __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
     extern __shared__ float4 smem[];
     const float4* dseg = a.dseg; const float4* nseg = a.nseg;
@@ -144,12 +147,18 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         if (__ballot_sync(FULL, active) == 0u) break;
 
         // ---- this iteration: every active lane either takes one step of the reference's loop or terminates ----
-        // loop condition of the reference tests the PREVIOUS step's dDirichlet (:206, Q5)
+        // reference: the loop condition tests the PREVIOUS step's dDirichlet (:206, Q5).
+        // physical:  the distance at the current position decides, and g is read at the closest boundary point.
+        int dir_arg = -1;
+        if (PHYS && active)
+            dD = a.dbvh.nodes ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, &dir_arg) : dirichlet_distance(dseg, a.n_dseg, x, y, &dir_arg);
         const bool stepping = active && steps < a.max_steps && dD > a.eps;
         if (active && !stepping) {
             // terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7)
+            float gx_ = x, gy_ = y;
+            if (PHYS && dir_arg >= 0) segment_closest_point(a.dseg[2 * dir_arg], a.dseg[2 * dir_arg + 1], x, y, gx_, gy_);
             float bc = 0.0f;
-            if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, x, y) : field_eval_inl(a.F.g, x, y);
+            if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, gx_, gy_) : field_eval_inl(a.F.g, gx_, gy_);
             if (DELTA) bc = bc * atten;
             a.walk_vals[id] = total_v + bc;
             if (TRACE) { if ((long long)id < a.n_trace) a.trace_len[id] = min(steps, a.trace_cap); }
@@ -160,11 +169,16 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         // ---- phase A: Dirichlet distance, direction --------------------------------------------------------------
         float dN = CUDART_INF_F, r = 0.f, dx = 0.f, dy = 0.f, ex = 0.f, ey = 0.f, ox = 0.f, oy = 0.f;
         bool want_ray = false, want_sil = false;
+        float gap = 0.0f;
         if (stepping) {
-            dD = a.dbvh.nodes ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, nullptr)
-                              : dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);      // :208
+            if (!PHYS)
+                dD = a.dbvh.nodes ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, nullptr)
+                                  : dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);      // :208
             uint32_t w0;
-            if (!SRC && !DELTA) {
+            if (PHYS) {
+                philox4x32_10(pidx, widx, (uint32_t)steps, 2u, a.key0, a.key1, o);      // stream tag 2: physical mode
+                w0 = o[0];
+            } else if (!SRC && !DELTA) {
                 // Laplace walks use one 32-bit word per step: one Philox block (stream tag 1) serves four steps
                 const int sel = steps & 3;
                 if (sel == 0) philox4x32_10(pidx, widx, (uint32_t)steps >> 2, 1u, a.key0, a.key1, o);
@@ -173,20 +187,31 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 philox4x32_10(pidx, widx, (uint32_t)steps, 0u, a.key0, a.key1, o);
                 w0 = o[0];
             }
-            float theta = (u24(w0) * 2.0f) * 3.14159274101257324f;                      // :226
-            if (NEU && onB) theta = theta / 2.0f + phi_n;                               // :227-228 (Q2)
+            float theta;
+            if (PHYS) {
+                // uniform direction; on a reflecting wall, uniform in the hemisphere around the inward normal
+                theta = (NEU && onB) ? phi_n + (u24(w0) - 0.5f) * 3.14159274101257324f : (u24(w0) * 2.0f) * 3.14159274101257324f;
+            } else {
+                theta = (u24(w0) * 2.0f) * 3.14159274101257324f;                        // :226
+                if (NEU && onB) theta = theta / 2.0f + phi_n;                           // :227-228 (Q2)
+            }
             sincosf(theta, &dy, &dx);                                                   // :230-232
             if (NEU) {
-                // intersect_polylines_jit prologue (:149-159): normalise, offset the origin by 1e-6
-                const float dn = norm2(dx, dy);
-                ex = dx / dn; ey = dy / dn;
-                ox = x + 1e-6f * ex; oy = y + 1e-6f * ey;
-                want_ray = ray_may_hit_disc(ox, oy, ex, ey, a.ndisc_x, a.ndisc_y, a.ndisc_r2);
+                if (PHYS) { ex = dx; ey = dy; ox = x; oy = y; }
+                else {
+                    // intersect_polylines_jit prologue (:149-159): normalise, offset the origin by 1e-6
+                    const float dn = norm2(dx, dy);
+                    ex = dx / dn; ey = dy / dn;
+                    ox = x + 1e-6f * ex; oy = y + 1e-6f * ey;
+                }
                 // the silhouette distance only matters if it can be smaller than dDirichlet (:212): every Neumann
                 // vertex is at least (|p - c| - R) away, so outside that margin min(dD, dN) = dD without looking.
                 const float gx = x - a.ndisc_x, gy = y - a.ndisc_y;
-                const float gap = sqrtf(gx * gx + gy * gy) - a.ndisc_r;
+                gap = sqrtf(gx * gx + gy * gy) - a.ndisc_r;
                 want_sil = TRACE || !(dD < gap * 0.9999f);
+                want_ray = ray_may_hit_disc(ox, oy, ex, ey, a.ndisc_x, a.ndisc_y, a.ndisc_r2);
+                // physical hits are limited to the star radius r <= max(dD, rmin): farther polylines cannot be hit
+                if (PHYS && gap > fmaxf(dD, a.rmin) + a.phys_nudge) want_ray = false;
             }
         }
 
@@ -212,20 +237,21 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                     dN2 = lane == src ? q : dN2;
                 }
             }
+            if (PHYS && a.neu_closed && want_sil) dN2 = fminf(dN2, closing_vertex_silhouette_sq(a.nseg, a.n_nseg, x, y));
             dN = sqrtf(dN2);
             need = __ballot_sync(FULL, want_ray);                                       // ray vs polyline (:162-178)
             if (a.nbvh.nodes) {
-                if (want_ray) bvh_ray_cast(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, ox, oy, ex, ey, best_s, best_k);
+                if (want_ray) bvh_ray_cast<PHYS>(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, ox, oy, ex, ey, best_s, best_k);
             } else if (__popc(need) > a.ray_coop_max) {
-                if (want_ray) ray_cast(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
+                if (want_ray) ray_cast<PHYS>(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
             } else {
                 while (need) {
                     const int src = __ffs(need) - 1; need &= need - 1u;
                     const float rox = __shfl_sync(FULL, ox, src), roy = __shfl_sync(FULL, oy, src);
                     const float rex = __shfl_sync(FULL, ex, src), rey = __shfl_sync(FULL, ey, src);
                     float cs; int ck;
-                    if (small) ray_cast_coop<true>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
-                    else ray_cast_coop<false>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
+                    if (small) ray_cast_coop<true, PHYS>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
+                    else ray_cast_coop<false, PHYS>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
                     best_s = lane == src ? cs : best_s; best_k = lane == src ? ck : best_k;
                 }
             }
@@ -238,8 +264,34 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         // ---- phase C: move, source sample, delta tracking ---------------------------------------------------------
         if (stepping) {
             float qx, qy;
+            if (PHYS && SRC) {
+                // source sample (physical): independent direction, rho^2/r^2 ~ -ln  <=>  rho ~ 4 rho ln(r/rho)/r^2 (the 2D
+                // disc Green's function), counted only if visible from x inside the star-shaped region
+                const float th2 = (NEU && onB) ? phi_n + (u24(o[1]) - 0.5f) * 3.14159274101257324f : (u24(o[1]) * 2.0f) * 3.14159274101257324f;
+                float s2, c2; sincosf(th2, &s2, &c2);
+                const float rho = r * sqrtf(u24p(o[2]) * u24p(o[3]));
+                bool vis = true;
+                if (NEU && gap <= rho && ray_may_hit_disc(x, y, c2, s2, a.ndisc_x, a.ndisc_y, a.ndisc_r2)) {
+                    float vs; int vk;
+                    if (a.nbvh.nodes) bvh_ray_cast<true>(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, x, y, c2, s2, vs, vk);
+                    else ray_cast<true>(nseg, a.n_nseg, x, y, c2, s2, vs, vk);
+                    vis = vk < 0 || vs > rho;
+                }
+                if (vis) total_v += field_eval_inl(a.F.f, x + rho * c2, y + rho * s2) * (r * r / 4.0f);
+            }
             if (NEU) {
-                if (best_k < 0 || best_s > r || best_s <= 0.0f) {                       // :166-174 miss
+                if (PHYS) {
+                    // a wall within r + nudge counts as hit, so a free step ends at least `nudge` short of every wall
+                    if (best_k < 0 || best_s > r + a.phys_nudge) { qx = x + r * ex; qy = y + r * ey; onB = false; }
+                    else {
+                        // reflect: sit `nudge` off the wall on the side we came from, remember that side's normal
+                        const float4 s1 = nseg[2 * best_k + 1];
+                        float nx = s1.x, ny = s1.y;
+                        if (nx * ex + ny * ey > 0.0f) { nx = -nx; ny = -ny; }
+                        qx = (x + best_s * ex) + a.phys_nudge * nx; qy = (y + best_s * ey) + a.phys_nudge * ny; onB = true;
+                        phi_n = atan2f(ny, nx);
+                    }
+                } else if (best_k < 0 || best_s > r || best_s <= 0.0f) {                // :166-174 miss
                     qx = x + r * ex; qy = y + r * ey; onB = false;
                 } else {                                                                // :176-197 hit
                     qx = ox + best_s * ex; qy = oy + best_s * ey; onB = true;
@@ -261,7 +313,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 sbgn = interior_probability(r * a.sqrt_sigma_bar);                      // sigma_bar * |G^sb|(r)
                 gn = sbgn * a.inv_sigma_bar;                                            // screenedGreensNorm2D (utils.py:29-44)
             }
-            if (SRC || DELTA) {                                                         // :242 (Q10: also without a source)
+            if (!PHYS && (SRC || DELTA)) {                                              // :242 (Q10: also without a source)
                 float rho;
                 if (DELTA) {                                                            // screened radius: inverse-CDF table (Q9)
                     const float pos = u24(o[2]) * (float)(a.icdf_len - 1);
@@ -596,20 +648,27 @@ static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + 
 
 typedef void (*walk_kernel_t)(const WalkArgs);
 template <bool TRACE>
-static walk_kernel_t pick_kernel(bool neu, bool src, bool delta) {
+static walk_kernel_t pick_kernel(bool neu, bool src, bool delta, bool phys) {
     const int m = (neu ? 4 : 0) | (src ? 2 : 0) | (delta ? 1 : 0);
+    if (phys) {                                        // physical mode: constant coefficients only (checked by the caller)
+        switch (m) {
+            case 0: return walk_kernel<false, false, false, TRACE, true>;
+            case 2: return walk_kernel<false, true, false, TRACE, true>;
+            case 4: return walk_kernel<true, false, false, TRACE, true>;
+            default: return walk_kernel<true, true, false, TRACE, true>;
+        }
+    }
     switch (m) {
-        case 0: return walk_kernel<false, false, false, TRACE>;
-        case 1: return walk_kernel<false, false, true, TRACE>;
-        case 2: return walk_kernel<false, true, false, TRACE>;
-        case 3: return walk_kernel<false, true, true, TRACE>;
-        case 4: return walk_kernel<true, false, false, TRACE>;
-        case 5: return walk_kernel<true, false, true, TRACE>;
-        case 6: return walk_kernel<true, true, false, TRACE>;
-        default: return walk_kernel<true, true, true, TRACE>;
+        case 0: return walk_kernel<false, false, false, TRACE, false>;
+        case 1: return walk_kernel<false, false, true, TRACE, false>;
+        case 2: return walk_kernel<false, true, false, TRACE, false>;
+        case 3: return walk_kernel<false, true, true, TRACE, false>;
+        case 4: return walk_kernel<true, false, false, TRACE, false>;
+        case 5: return walk_kernel<true, false, true, TRACE, false>;
+        case 6: return walk_kernel<true, true, false, TRACE, false>;
+        default: return walk_kernel<true, true, true, TRACE, false>;
     }
 }
-
 
 // =================================================================================================
 // C ABI
@@ -694,6 +753,8 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         for (int k = 0; k < 2 * nn; ++k) scale = std::fmax(scale, std::fabs((double)nxy[k]));
         const float inflate = (float)(1e-5 * scale + 1e-30);
         s->bvh_slack = (float)(1e-4 * scale + 1e-30);
+        s->phys_nudge = (float)(1e-5 * scale);
+        s->neu_closed = (nn >= 4 && nxy[0] == nxy[2 * nn - 2] && nxy[1] == nxy[2 * nn - 1]) ? 1 : 0;
         cudaError_t be = cudaSuccess;
         if (s->n_dseg >= env_int("WOST_BVH_MIN_DIRICHLET", 48)) {
             const std::vector<float4> nodes = build_bvh(dxy, nd, inflate, &s->dbvh_leaves);
@@ -829,6 +890,9 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     if (n_pts >= (1ll << 32) || P->n_walks + P->walk_offset >= (1ll << 32) || n_pts + P->point_index_base >= (1ll << 32))
         return fail(WOST_ERR_INVALID, "point and walk indices must fit 32 bits (Philox counter words)");
     const bool delta = P->delta_tracking != 0;
+    if (P->compat_mode != WOST_COMPAT_REFERENCE && P->compat_mode != WOST_COMPAT_PHYSICAL) return fail(WOST_ERR_INVALID, "unknown compat_mode");
+    if (P->compat_mode == WOST_COMPAT_PHYSICAL && delta)
+        return fail(WOST_ERR_UNSUPPORTED, "physical mode covers constant coefficients only (no delta tracking)");
     if (delta) {
         if (!(P->sigma_bar > 0.0f)) return fail(WOST_ERR_INVALID, "delta tracking needs sigma_bar > 0");
         if (!P->screened_icdf || P->icdf_len < 2) return fail(WOST_ERR_INVALID, "delta tracking needs the screened radius table");
@@ -895,14 +959,15 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
         if (a.ray_coop_max > 32) a.ray_coop_max = 32;
     }
     a.dbvh.nodes = scene->dbvh; a.dbvh.n_leaves = scene->dbvh_leaves; a.nbvh.nodes = scene->nbvh; a.nbvh.cones = scene->ncones; a.nbvh.n_leaves = scene->nbvh_leaves;
-    a.bvh_slack = scene->bvh_slack;
+    a.bvh_slack = scene->bvh_slack; a.neu_closed = scene->neu_closed; a.phys_nudge = scene->phys_nudge;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;
     const size_t seg_bytes = sizeof(float4) * 2 * ((size_t)scene->n_dseg + scene->n_nseg);
     a.stage_smem = seg_bytes <= 96 * 1024 ? 1 : 0;
     const size_t smem = a.stage_smem ? seg_bytes : 0;
-    walk_kernel_t kern = trace ? pick_kernel<true>(neu, src, delta) : pick_kernel<false>(neu, src, delta);
+    const bool phys = P->compat_mode == WOST_COMPAT_PHYSICAL;
+    walk_kernel_t kern = trace ? pick_kernel<true>(neu, src, delta, phys) : pick_kernel<false>(neu, src, delta, phys);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, threads, smem));

@@ -42,6 +42,8 @@ class Scenario:
     def delta(self) -> bool:
         return self.alpha is not None or self.sigma is not None
 
+    compat: str = "reference"               # "physical" for the textbook-WoSt validation scenes below
+
     def make_solver(self, **kw):
         """The product solver (``solvers.WoStSolver.WostSolver_2D``) for this scenario."""
         from .geometry.PolylinesSimple import PolyLinesSimple
@@ -50,7 +52,7 @@ class Scenario:
         mode = "ratio" if (self.delta and self.sp_mode == SP_RATIO) else "auto"
         return WostSolver_2D(PolyLinesSimple(self.dirichlet), self.g,
                              PolyLinesSimple(self.neumann) if self.neumann is not None else None,
-                             self.f, self.sigma, self.alpha, sigma_prime_mode=mode, **kw)
+                             self.f, self.sigma, self.alpha, sigma_prime_mode=mode, compat=self.compat, **kw)
 
 
 def square(half: float) -> torch.Tensor:
@@ -218,4 +220,48 @@ def cfg2_throughput(n_points: int = 65536, n_walks: int = 1024) -> Scenario:
     return s
 
 
+# ---- analytic mixed-boundary problems for compat="physical" (SURVEY §4 iv; not in the reference) -------------------
+def _unit_square_neumann_top():
+    dirichlet = torch.tensor([[0.0, 1.0], [0.0, 0.0], [1.0, 0.0], [1.0, 1.0]])       # left, bottom, right edges
+    neumann = torch.tensor([[1.0, 1.0], [0.0, 1.0]])                                 # top edge, du/dy = 0
+    pts = torch.tensor([[0.5, 0.5], [0.3, 0.8], [0.7, 0.95], [0.2, 0.3], [0.5, 0.99], [0.9, 0.6], [0.1, 0.9], [0.6, 0.2]])
+    return dirichlet, neumann, pts
+
+
+def phys_laplace_neumann_top() -> Scenario:
+    """Harmonic u = sin(pi x) cosh(pi (y-1)) / cosh(pi) on the unit square: du/dy = 0 on the top edge."""
+    from .fields import GridField
+
+    d, n, pts = _unit_square_neumann_top()
+    g = GridField.from_callable(lambda p: torch.sin(math.pi * p[0]) * torch.cosh(math.pi * (p[1] - 1.0)) / math.cosh(math.pi),
+                                [[0.0, 1.0], [0.0, 1.0]], n=513)
+    return Scenario(name="phys_laplace_neumann_top", dirichlet=d, neumann=n, points=pts, g=g, n_walks=20000, max_steps=1000,
+                    eps=1e-4, compat="physical",
+                    analytic=lambda p: torch.sin(math.pi * p[:, 0]) * torch.cosh(math.pi * (p[:, 1] - 1.0)) / math.cosh(math.pi))
+
+
+def phys_poisson_neumann_top() -> Scenario:
+    """u = cos(pi (1-y)):  -lap u = pi^2 cos(pi (1-y)),  du/dy = 0 on the top edge."""
+    d, n, pts = _unit_square_neumann_top()
+    pi = float(np.float32(math.pi))
+    g = TermField(0.0, [make_term(A=1.0, trig1=("cos", 0.0, -pi, pi))])
+    f = TermField(0.0, [make_term(A=math.pi ** 2, trig1=("cos", 0.0, -pi, pi))])
+    return Scenario(name="phys_poisson_neumann_top", dirichlet=d, neumann=n, points=pts, g=g, f=f, n_walks=20000,
+                    max_steps=1000, eps=1e-4, compat="physical", analytic=lambda p: torch.cos(math.pi * (1.0 - p[:, 1])))
+
+
+def phys_cylinder(n_seg: int = 256) -> Scenario:
+    """Potential flow around a cylinder: u = x (1 + R^2/r^2) is harmonic with du/dr = 0 on r = R = 0.5.
+    Dirichlet square +-2, Neumann n_seg-gon (>= 192 segments exercises the BVH + silhouette cones)."""
+    from .fields import GridField
+
+    R = 0.5
+    g = GridField.from_callable(lambda p: p[0] * (1.0 + R * R / (p[0] ** 2 + p[1] ** 2 + 1e-12)), [[-2.0, 2.0], [-2.0, 2.0]], n=1025)
+    pts = torch.tensor([[0.8, 0.1], [0.0, 0.7], [-1.2, 0.9], [0.55, 0.0], [1.5, -1.0], [-0.6, -0.3], [0.4, 0.4], [1.9, 1.9]])
+    return Scenario(name=f"phys_cylinder_{n_seg}", dirichlet=square(2.0), neumann=ngon(R, n_seg).flip(0).contiguous(), points=pts, g=g,
+                    n_walks=20000, max_steps=2000, eps=1e-4, compat="physical",
+                    analytic=lambda p: p[:, 0] * (1.0 + R * R / (p[:, 0] ** 2 + p[:, 1] ** 2)))
+
+
+PHYSICAL = {"phys_laplace": phys_laplace_neumann_top, "phys_poisson": phys_poisson_neumann_top, "phys_cylinder": phys_cylinder}
 ALL = {"cfg1a": cfg1a, "cfg1b": cfg1b, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}

@@ -51,11 +51,21 @@ class WostSolver_2D:
     def __init__(self, dirichletBoundary: PolyLines, dirichletBoundaryFunction: callable = None,
                  neumannBoundary: PolyLines = None, source: callable = None, sigma: callable = None,
                  alpha: callable = None, *, field_resolution: int = 257, sigma_prime_resolution: int = 65,
-                 sigma_prime_mode: str = "auto"):
+                 sigma_prime_mode: str = "auto", compat: str = "reference"):
         """``sigma_prime_mode``: ``"auto"`` differentiates the coefficients like the reference and falls back to
         ``sigma/alpha`` when that fails; ``"ratio"`` forces the fallback — what the reference ends up with for
         callables that wrap their result in ``torch.tensor(...)`` (tests/testWostVariableCoefficients.py:49,57,
-        SURVEY Q12) — and ``"full"`` insists on the differentiated form."""
+        SURVEY Q12) — and ``"full"`` insists on the differentiated form.
+
+        ``compat``: ``"reference"`` (default) reproduces the reference's estimator, quirks included (SURVEY §0);
+        ``"physical"`` runs textbook Walk on Stars for constant coefficients — first hit by ray distance, reflection
+        into the hemisphere facing the domain, the closing vertex of a closed loop is a silhouette candidate,
+        termination projects onto the Dirichlet boundary, Green's-function source sampling with visibility.  It is not
+        part of the reference (whose mixed-boundary walks leak through Neumann walls, Q1/Q2) and is validated against
+        analytic mixed-boundary solutions instead."""
+        if compat not in nat.COMPAT:
+            raise ValueError("compat must be 'reference' or 'physical'")
+        self.compat = compat
         if sigma_prime_mode not in ("auto", "ratio", "full"):
             raise ValueError("sigma_prime_mode must be 'auto', 'ratio' or 'full'")
         self.sigma_prime_mode = sigma_prime_mode
@@ -259,7 +269,8 @@ class WostSolver_2D:
                         delta=self.use_delta_tracking, sp_mode=self.sp_mode,
                         sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
                         point_index_base=point_index_base, walk_offset=walk_offset, want_block_stats=want_block_stats,
-                        want_walk_vals=want_walk_vals, n_trace=n_trace, trace_cap=trace_cap, device_outputs=device_outputs)
+                        want_walk_vals=want_walk_vals, n_trace=n_trace, trace_cap=trace_cap, device_outputs=device_outputs,
+                        compat=self.compat)
         res["seed"] = seed
         return res
 

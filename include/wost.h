@@ -82,6 +82,16 @@ enum {
     WOST_SP_FIELD = 2    /* fields.sigma_prime is sigma' itself (tabulated)                                  */
 };
 
+/* which estimator wost_solve runs */
+enum {
+    WOST_COMPAT_REFERENCE = 0,  /* the reference's walk, quirks included — the parity mode                   */
+    WOST_COMPAT_PHYSICAL = 1    /* textbook Walk on Stars for constant coefficients (no delta tracking): hits by true ray   */
+                                /* distance, reflection into the hemisphere facing the domain, closing vertex of closed     */
+                                /* loops is a silhouette candidate, termination projects onto the Dirichlet boundary,       */
+                                /* source radius from the disc Green's function with an independent direction, visibility   */
+                                /* tested.  Not in the reference; validated against analytic mixed-boundary solutions.      */
+};
+
 typedef struct {
     const wost_field_t* g;            /* Dirichlet data (boundaryDirichlet, :45-48,295); NULL = 0  */
     const wost_field_t* f;            /* source (:50,242-258); NULL = no source                     */
@@ -102,7 +112,8 @@ typedef struct {
     uint64_t seed;            /* Philox4x32-10 key                                                 */
     int64_t point_index_base; /* global index of pts[0]  } Philox counter = (point, walk, step, 0) */
     int64_t walk_offset;      /* global index of walk 0  }  => results independent of sharding     */
-    int32_t reserved[4];
+    int32_t compat_mode;      /* WOST_COMPAT_*                                                     */
+    int32_t reserved[3];
 } wost_solve_params_t;
 
 #define WOST_WALK_BLOCK 1024   /* walks per deterministic reduction block */

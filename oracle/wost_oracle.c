@@ -266,8 +266,8 @@ static int field_masked_out(const orc_field_t* f, float x, float y) {
 
 static void grid_cell(const orc_field_t* f, float x, float y, int* i, int* j, float* tx, float* ty) {
     float fx = (x - f->x0) / f->dx, fy = (y - f->y0) / f->dy;
-    fx = fx < 0.0f ? 0.0f : (fx > (float)(f->nx - 1) ? (float)(f->nx - 1) : fx);
-    fy = fy < 0.0f ? 0.0f : (fy > (float)(f->ny - 1) ? (float)(f->ny - 1) : fy);
+    fx = fminf(fmaxf(fx, 0.0f), (float)(f->nx - 1));    /* fmaxf/fminf drop NaN: a diverged walker reads the table edge */
+    fy = fminf(fmaxf(fy, 0.0f), (float)(f->ny - 1));
     int ii = (int)fx, jj = (int)fy;
     if (ii > f->nx - 2) ii = f->nx - 2;
     if (jj > f->ny - 2) jj = f->ny - 2;
@@ -574,11 +574,95 @@ static float run_walk(const orc_params_t* p, walk_rng_t* g, float x0, float y0, 
     return total;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * "Physical" mode: textbook Walk on Stars (Sawhney, Miller, Gkioulekas, Crane 2023) for constant coefficients.
+ * Not part of the reference (whose mixed-boundary walks leak); shares its primitives.
+ * ---------------------------------------------------------------------------------------- */
+static float phys_distance(const float* pts, int n, float px, float py, float* cxo, float* cyo) {
+    float best = INFINITY; *cxo = px; *cyo = py;
+    for (int k = 0; k + 1 < n; ++k) {
+        float ax = pts[2 * k], ay = pts[2 * k + 1], bx = pts[2 * k + 2], by = pts[2 * k + 3];
+        float ux = bx - ax, uy = by - ay, vx = px - ax, vy = py - ay;
+        float t = (vx * ux + vy * uy) / (ux * ux + uy * uy);
+        t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+        float cx = (1.0f - t) * ax + t * bx, cy = (1.0f - t) * ay + t * by;
+        float q = fmaf(cy - py, cy - py, (cx - px) * (cx - px));
+        if (q < best) { best = q; *cxo = cx; *cyo = cy; }
+    }
+    return sqrtf(best);
+}
+/* silhouette distance including the closing vertex of a closed loop */
+static float phys_silhouette_distance(const float* pts, int n, float px, float py) {
+    float best = orc_silhouette_distance(pts, n, px, py);
+    if (n >= 4 && pts[0] == pts[2 * n - 2] && pts[1] == pts[2 * n - 1]) {
+        float ax = pts[2 * n - 4], ay = pts[2 * n - 3], bx = pts[0], by = pts[1], cx = pts[2], cy = pts[3];
+        float c1 = cross2(bx - ax, by - ay, px - ax, py - ay), c2 = cross2(cx - bx, cy - by, px - bx, py - by);
+        if (c1 * c2 < 0.0f) { float d = norm2f(bx - px, by - py); if (d < best) best = d; }
+    }
+    return best;
+}
+/* first hit by true ray distance t within tmax; returns segment or -1 */
+static int phys_ray(const float* pts, int n, float ox, float oy, float ex, float ey, float tmax, float* t_hit) {
+    float best = INFINITY; int idx = -1;
+    for (int k = 0; k + 1 < n; ++k) {
+        float ax = pts[2 * k], ay = pts[2 * k + 1], ux = pts[2 * k + 2] - ax, uy = pts[2 * k + 3] - ay, wx = ox - ax, wy = oy - ay;
+        float d = cross2(ex, ey, ux, uy);
+        float s = cross2(ex, ey, wx, wy) / d, t = cross2(ux, uy, wx, wy) / d;
+        if ((s >= 0.0f) && (s <= 1.0f) && (t > 0.0f) && t < best) { best = t; idx = k; }
+    }
+    if (idx < 0 || best > tmax) return -1;
+    *t_hit = best;
+    return idx;
+}
+
+static float run_walk_physical(const orc_params_t* p, walk_rng_t* g, float x0, float y0, uint32_t pidx, uint32_t widx,
+                               int32_t* n_steps, int32_t trace_cap, float* trace, int32_t* trace_len) {
+    const int has_neu = p->neu_pts && p->n_neu > 0, has_src = p->f != NULL;
+    const float rmin = (float)((double)p->eps / 2.0), eps = p->eps;
+    float x = x0, y = y0, total = 0.0f, phi_in = 0.0f, cx = x0, cy = y0, dD;
+    int onB = 0, steps = 0;
+    for (;;) {
+        dD = phys_distance(p->dir_pts, p->n_dir, x, y, &cx, &cy);
+        if (!(steps < p->max_steps && dD > eps)) break;
+        float dN = has_neu ? phys_silhouette_distance(p->neu_pts, p->n_neu, x, y) : INFINITY;
+        float m = dN < dD ? dN : dD, r = m > rmin ? m : rmin;
+        if (trace && steps < trace_cap) { float* t = trace + 4 * steps; t[0] = x; t[1] = y; t[2] = dD; t[3] = dN; }
+        orc_philox4x32_10(pidx, widx, (uint32_t)steps, 2u, g->k0, g->k1, g->o);
+        /* direction: uniform, or uniform in the hemisphere around the inward normal when sitting on the wall */
+        float theta = onB ? phi_in + (u24(g->o[0]) - 0.5f) * 3.14159274101257324f : (u24(g->o[0]) * 2.0f) * 3.14159274101257324f;
+        float ex = cosf(theta), ey = sinf(theta);
+        if (has_src) {
+            float th2 = onB ? phi_in + (u24(g->o[1]) - 0.5f) * 3.14159274101257324f : (u24(g->o[1]) * 2.0f) * 3.14159274101257324f;
+            float sx_ = cosf(th2), sy_ = sinf(th2);
+            float rho = r * sqrtf(u24p(g->o[2]) * u24p(g->o[3]));        /* rho^2/r^2 has pdf -ln: rho pdf 4 rho ln(r/rho)/r^2 */
+            float th; int vis = 1;
+            if (has_neu) vis = phys_ray(p->neu_pts, p->n_neu, x, y, sx_, sy_, rho, &th) < 0;
+            if (vis) total += orc_field_eval(p->f, x + rho * sx_, y + rho * sy_) * (r * r / 4.0f);
+        }
+        /* a wall within r + nudge counts as hit, so a free step always ends at least `nudge` short of every wall
+         * (fp32 rounding of x + r e is ~1e-7 of the scene scale, the nudge 1e-5) */
+        float t_hit; int k = has_neu ? phys_ray(p->neu_pts, p->n_neu, x, y, ex, ey, r + p->phys_nudge, &t_hit) : -1;
+        if (k >= 0) {
+            float ux = p->neu_pts[2 * k + 2] - p->neu_pts[2 * k], uy = p->neu_pts[2 * k + 3] - p->neu_pts[2 * k + 1];
+            float len = norm2f(ux, uy), nx = -uy / len, ny = ux / len;
+            if (nx * ex + ny * ey > 0.0f) { nx = -nx; ny = -ny; }        /* face the side the walker came from */
+            x = (x + t_hit * ex) + p->phys_nudge * nx; y = (y + t_hit * ey) + p->phys_nudge * ny;   /* sit `nudge` off the wall */
+            phi_in = atan2f(ny, nx); onB = 1;
+        } else { x = x + r * ex; y = y + r * ey; onB = 0; }
+        ++steps;
+    }
+    total += p->g ? orc_field_eval(p->g, cx, cy) : 0.0f;                /* g at the closest Dirichlet point */
+    *n_steps = steps;
+    if (trace_len) *trace_len = steps < trace_cap ? steps : trace_cap;
+    return total;
+}
+
 int orc_solve(const orc_params_t* p, const float* pts, int64_t n_pts,
               double* mean, double* m2, float* walk_vals, int64_t* steps_total, int32_t* walk_steps,
               int64_t n_trace, int32_t trace_cap, float* trace, int32_t* trace_len) {
     const int64_t W = p->n_walks;
     int64_t steps_sum = 0;
+    if (p->compat_mode == 1 && (p->rng_mode != ORC_RNG_PHILOX || p->delta)) return -1;   /* physical: Philox, constant coefficients */
     if (p->rng_mode == ORC_RNG_MT) {
         /* one sequential stream over all points and walks, like the reference */
         mt_t torch_rng, np_rng; mt_seed(&torch_rng, (uint32_t)p->seed); mt_seed(&np_rng, (uint32_t)p->seed_numpy);
@@ -618,9 +702,10 @@ int orc_solve(const orc_params_t* p, const float* pts, int64_t n_pts,
             for (int64_t w = 0; w < W; ++w) {
                 int64_t flat = pi * W + w; int32_t ns;
                 float* tr = (trace && flat < n_trace) ? trace + (size_t)flat * trace_cap * 4 : NULL;
-                float v = run_walk(p, &g, pts[2 * pi], pts[2 * pi + 1], (uint32_t)(p->point_index_base + pi),
-                                   (uint32_t)(p->walk_offset + w), NULL, &ns, trace_cap, tr,
-                                   (trace_len && flat < n_trace) ? trace_len + flat : NULL);
+                int32_t* tl = (trace_len && flat < n_trace) ? trace_len + flat : NULL;
+                float v = p->compat_mode == 1
+                    ? run_walk_physical(p, &g, pts[2 * pi], pts[2 * pi + 1], (uint32_t)(p->point_index_base + pi), (uint32_t)(p->walk_offset + w), &ns, trace_cap, tr, tl)
+                    : run_walk(p, &g, pts[2 * pi], pts[2 * pi + 1], (uint32_t)(p->point_index_base + pi), (uint32_t)(p->walk_offset + w), NULL, &ns, trace_cap, tr, tl);
                 vals[w] = v; if (walk_steps) walk_steps[flat] = ns;
                 steps_sum += ns; s += v;
             }

@@ -49,7 +49,7 @@ class _Params(C.Structure):
                 ("rng_mode", C.c_int32), ("seed", C.c_uint64), ("seed_numpy", C.c_uint64),
                 ("point_index_base", C.c_int64), ("walk_offset", C.c_int64),
                 ("icdf", C.c_void_p), ("icdf_len", C.c_int32), ("n_threads", C.c_int32),
-                ("sincos_fn", C.c_void_p), ("atan2_fn", C.c_void_p)]
+                ("sincos_fn", C.c_void_p), ("atan2_fn", C.c_void_p), ("compat_mode", C.c_int32), ("phys_nudge", C.c_float)]
 
 
 SINCOS_FN = C.CFUNCTYPE(None, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float))
@@ -269,11 +269,12 @@ class Problem:
 
     @classmethod
     def from_scenario(cls, s, sigma_bar=None):
+        """(pass ``compat=s.compat`` to :meth:`solve` for the physical-mode scenes)"""
         sb = sigma_bar if sigma_bar is not None else (s.sigma_bar or 0.0)
         return cls(s.dirichlet, s.neumann, g=s.g, f=s.f, alpha=s.alpha, sigma=s.sigma, sigma_bar=sb, sp_mode=s.sp_mode)
 
     def params(self, n_walks, max_steps, eps, rng_mode, seed, seed_numpy=0, point_index_base=0, walk_offset=0,
-               icdf=None, n_threads=0, torch_trig=False):
+               icdf=None, n_threads=0, torch_trig=False, compat="reference"):
         p = _Params()
         p.dir_pts, p.n_dir = self.dir.ctypes.data, len(self.dir)
         p.neu_pts, p.n_neu = (self.neu.ctypes.data, len(self.neu)) if self.neu is not None else (None, 0)
@@ -292,6 +293,9 @@ class Problem:
             self._icdf_live = _f32(icdf)
             p.icdf, p.icdf_len = self._icdf_live.ctypes.data, len(self._icdf_live)
         p.n_threads = int(n_threads)
+        p.compat_mode = {"reference": 0, "physical": 1}[compat]
+        scale = float(np.abs(self.dir).max()) if self.neu is None else float(max(np.abs(self.dir).max(), np.abs(self.neu).max()))
+        p.phys_nudge = np.float32(1e-5 * scale)
         if torch_trig:
             self._trig = torch_trig_callbacks()
             p.sincos_fn, p.atan2_fn = C.cast(self._trig[0], C.c_void_p), C.cast(self._trig[1], C.c_void_p)
@@ -303,10 +307,10 @@ class Problem:
 
     def solve(self, points, n_walks, max_steps=1000, eps=1e-4, rng_mode=RNG_PHILOX, seed=42, seed_numpy=42,
               point_index_base=0, walk_offset=0, icdf=None, n_threads=0, walk_vals=False, walk_steps=False,
-              n_trace=0, trace_cap=0, torch_trig=False):
+              n_trace=0, trace_cap=0, torch_trig=False, compat="reference"):
         pts = _f32(points).reshape(-1, 2)
         P = len(pts)
-        p = self.params(n_walks, max_steps, eps, rng_mode, seed, seed_numpy, point_index_base, walk_offset, icdf, n_threads, torch_trig)
+        p = self.params(n_walks, max_steps, eps, rng_mode, seed, seed_numpy, point_index_base, walk_offset, icdf, n_threads, torch_trig, compat)
         mean, m2 = np.zeros(P, np.float64), np.zeros(P, np.float64)
         vals = np.zeros((P, n_walks), np.float32) if walk_vals else None
         wst = np.zeros((P, n_walks), np.int32) if walk_steps else None

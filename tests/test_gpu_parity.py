@@ -489,3 +489,42 @@ def test_tabulated_fields_and_sigma_prime_field_path_match_oracle():
     # sigma' table vs the closed form of the true alpha
     q = torch.tensor([0.3, -0.2])
     assert float(sp_grid(q)) == pytest.approx(float(solver.sigma_prime(q)), rel=2e-2, abs=2e-3)
+
+
+# ---- compat="physical": textbook WoSt (not in the reference), validated against the oracle and analytic solutions ----
+@pytest.mark.parametrize("key", ["phys_laplace", "phys_poisson", "phys_cylinder"])
+def test_physical_mode_kernel_matches_oracle_and_analytic(key):
+    s = sc.PHYSICAL[key]()
+    solver = s.make_solver()
+    assert solver.compat == "physical"
+    W = 256
+    r = solver.solve_raw(s.points, W, s.max_steps, s.eps, seed=77, want_walk_vals=True, n_trace=len(s.points) * W, trace_cap=6)
+    o = orc.Problem.from_scenario(s).solve(s.points, W, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=77, compat="physical",
+                                           walk_vals=True, n_trace=len(s.points) * W, trace_cap=6)
+    n3 = np.minimum(np.minimum(r["trace_len"], o["trace_len"]), 3)
+    for i in range(len(n3)):
+        assert np.allclose(r["trace"][i, : n3[i]], o["trace"][i, : n3[i]], rtol=1e-5, atol=2e-5), (key, i)
+    dv = np.abs(r["walk_vals"] - o["walk_vals"])
+    assert (dv <= 2e-3 * (1 + np.abs(o["walk_vals"]))).mean() > 0.85, (key, (dv <= 2e-3 * (1 + np.abs(o["walk_vals"]))).mean())
+    assert abs(int(r["steps"][0]) - o["steps"]) <= 0.05 * o["steps"]
+    # analytic solution at a large walk count
+    nw = 200000
+    est, stats = solver.solve(s.points, nWalks=nw, maxSteps=s.max_steps, eps=s.eps, seed=5, return_stats=True)
+    exact = s.analytic(s.points).double()
+    slack = 2e-4 if key != "phys_cylinder" else 1e-3                    # eps shell; 256-gon instead of a circle
+    z = (est[:, 0].double() - exact).abs() / (stats["stderr"] + slack)
+    assert torch.all(z <= 3.5), z
+    assert torch.sqrt(((est[:, 0].double() - exact) ** 2).mean()) < 5e-3
+
+
+def test_physical_mode_dirichlet_only_and_unsupported_combinations():
+    s = sc.cfg3()                                                       # Poisson, Dirichlet only: both modes are unbiased
+    s.compat = "physical"
+    est, stats = s.make_solver().solve(s.points[::8], nWalks=100000, maxSteps=s.max_steps, eps=s.eps, seed=3, return_stats=True)
+    z = (est[:, 0].double() - s.analytic(s.points[::8]).double()).abs() / (stats["stderr"] + 2e-4)
+    assert torch.all(z <= 3.5), z
+    d = sc.cfg1b()
+    with pytest.raises(nat.WostError, match="constant coefficients"):
+        WostSolver_2D(PolyLinesSimple(d.dirichlet), d.g, None, d.f, d.sigma, d.alpha, compat="physical").solve(d.points, nWalks=8)
+    with pytest.raises(ValueError):
+        WostSolver_2D(PolyLinesSimple(d.dirichlet), compat="textbook")

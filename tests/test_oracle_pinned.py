@@ -191,3 +191,19 @@ def test_analytic_solutions():
         exact = s.analytic(s.points[::5]).numpy()
         z = (r["mean"] - exact) / (r["stderr"] + 1e-4)                   # 1e-4: the eps-shell bias of the estimator
         assert np.mean(np.abs(z) <= tol) >= 0.95, z
+
+
+# ---- "physical" mode (textbook WoSt, not in the reference): analytic mixed-boundary solutions ---------------------
+@pytest.mark.parametrize("key", ["phys_laplace", "phys_poisson", "phys_cylinder"])
+def test_physical_mode_matches_analytic_mixed_boundary_solutions(key):
+    s = sc.PHYSICAL[key]() if key != "phys_cylinder" else sc.phys_cylinder(64)
+    nw = 30000
+    r = orc.Problem.from_scenario(s).solve(s.points, nw, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=11, compat="physical")
+    exact = s.analytic(s.points).numpy()
+    slack = 2e-4 if key != "phys_cylinder" else 2e-3                    # eps shell; polygonal cylinder
+    z = np.abs(r["mean"] - exact) / (r["stderr"] + slack)
+    assert np.all(z <= 3.5), z
+    # the reference's estimator does NOT solve these problems (walks leak through the Neumann wall)
+    ref = orc.Problem.from_scenario(s).solve(s.points, nw, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=11, compat="reference")
+    zr = np.abs(ref["mean"] - exact) / (ref["stderr"] + slack)
+    assert not np.all(np.isfinite(zr)) or np.max(zr) > 5.0
