@@ -924,9 +924,15 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
         (rc = s_tlen.init(out_trace_len, trace ? n_trace : 0, true, st))) return rc;
 
     // scratch: per-walk totals (unless the caller wants them), counters, block statistics
+    // The per-walk buffer is bounded: evaluation points are processed in passes of at most WOST_MAX_WALK_VALS walks
+    // (default 2^29 = 2 GiB of fp32), so arbitrarily large jobs run in constant scratch memory.
+    long long max_vals = 1ll << 29;
+    if (const char* e = std::getenv("WOST_MAX_WALK_VALS")) max_vals = std::max(1ll, std::atoll(e));
+    if (W > max_vals) max_vals = W;                                     // at least one point per pass
+    const long long pts_per_pass = std::max(1ll, std::min((long long)n_pts, max_vals / W));
     float* vals = nullptr; bool vals_temp = false;
-    if (out_walk_vals && is_device_ptr(out_walk_vals)) vals = out_walk_vals;
-    else { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)n_pts * W, st)); vals_temp = true; }
+    const bool vals_dev_out = out_walk_vals && is_device_ptr(out_walk_vals);
+    if (!vals_dev_out) { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)pts_per_pass * W, st)); vals_temp = true; }
     unsigned long long* ctrs = nullptr;
     CU(cudaMallocAsync((void**)&ctrs, 2 * sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(ctrs, 0, 2 * sizeof(unsigned long long), st));
@@ -972,27 +978,39 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, threads, smem));
     if (occ < 1) return fail(WOST_ERR_CUDA, "walk kernel does not fit on an SM");
-    const long long total = (long long)n_pts * W;
-    long long grid = (long long)scene->sm_count * occ;                 // persistent: one wave, a multiple of the SM count
-    const long long want = (total + threads - 1) / threads;
-    if (grid > want) grid = want;
-    const long long nwarps = grid * (threads / 32);
-    long long chunk = total / (nwarps * 8);
-    a.chunk = (int)(chunk < 32 ? 32 : (chunk > 1024 ? 1024 : chunk));
-    if (total < nwarps * 32) a.chunk = (int)((total + nwarps - 1) / nwarps);
-    if (a.chunk < 1) a.chunk = 1;
-
-    kern<<<(unsigned)grid, threads, smem, st>>>(a);
-    CU(cudaGetLastError());
-    block_stats_kernel<<<blocks_for(n_pts * nblk * 32, 256), 256, 0, st>>>(vals, n_pts, W, nblk, blk);
-    CU(cudaGetLastError());
+    for (long long p0 = 0; p0 < n_pts; p0 += pts_per_pass) {
+        const long long np = std::min(pts_per_pass, (long long)n_pts - p0);
+        const long long total = np * W;
+        long long grid = (long long)scene->sm_count * occ;             // persistent: one wave, a multiple of the SM count
+        const long long want = (total + threads - 1) / threads;
+        if (grid > want) grid = want;
+        const long long nwarps = grid * (threads / 32);
+        long long chunk = total / (nwarps * 8);
+        a.chunk = (int)(chunk < 32 ? 32 : (chunk > 1024 ? 1024 : chunk));
+        if (total < nwarps * 32) a.chunk = (int)((total + nwarps - 1) / nwarps);
+        if (a.chunk < 1) a.chunk = 1;
+        a.pts = s_pts.dev + 2 * p0; a.n_pts = np; a.point_index_base = P->point_index_base + p0;
+        a.walk_vals = vals_dev_out ? out_walk_vals + (size_t)p0 * W : vals;
+        if (trace) {                                                    // the first n_trace walks in point-major order
+            const long long first = p0 * W;
+            a.n_trace = std::max(0ll, std::min((long long)n_trace - first, total));
+            a.trace = s_trace.dev + (size_t)first * trace_cap * 4; a.trace_len = s_tlen.dev + first;
+        }
+        if (p0 > 0) CU(cudaMemsetAsync(ctrs, 0, sizeof(unsigned long long), st));   // walk counter only; steps accumulate
+        kern<<<(unsigned)grid, threads, smem, st>>>(a);
+        CU(cudaGetLastError());
+        block_stats_kernel<<<blocks_for(np * nblk * 32, 256), 256, 0, st>>>(a.walk_vals, np, W, nblk, blk + 2 * p0 * nblk);
+        CU(cudaGetLastError());
+        if (out_walk_vals && vals_temp)
+            CU(cudaMemcpyAsync(out_walk_vals + (size_t)p0 * W, vals, sizeof(float) * (size_t)np * W, cudaMemcpyDeviceToHost, st));
+    }
     if (s_mean.dev || s_m2.dev) {
         merge_stats_kernel<<<blocks_for(n_pts, 128), 128, 0, st>>>(blk, n_pts, W, nblk, s_mean.dev, s_m2.dev);
         CU(cudaGetLastError());
     }
     if (s_steps.dev) CU(cudaMemcpyAsync(s_steps.dev, ctrs + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     bool sync = s_mean.host_out() || s_m2.host_out() || s_blk.host_out() || s_steps.host_out() || s_trace.host_out() || s_tlen.host_out();
-    if (out_walk_vals && vals_temp) { CU(cudaMemcpyAsync(out_walk_vals, vals, sizeof(float) * (size_t)n_pts * W, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (out_walk_vals && vals_temp) sync = true;
     if ((rc = s_pts.finish()) || (rc = s_icdf.finish()) || (rc = s_mean.finish()) || (rc = s_m2.finish()) || (rc = s_blk.finish()) ||
         (rc = s_steps.finish()) || (rc = s_trace.finish()) || (rc = s_tlen.finish())) return rc;
     if (vals_temp) CU(cudaFreeAsync(vals, st));

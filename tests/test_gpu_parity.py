@@ -528,3 +528,21 @@ def test_physical_mode_dirichlet_only_and_unsupported_combinations():
         WostSolver_2D(PolyLinesSimple(d.dirichlet), d.g, None, d.f, d.sigma, d.alpha, compat="physical").solve(d.points, nWalks=8)
     with pytest.raises(ValueError):
         WostSolver_2D(PolyLinesSimple(d.dirichlet), compat="textbook")
+
+
+def test_bounded_scratch_passes_give_identical_bits(monkeypatch):
+    """Large jobs are processed in passes over the evaluation points with a bounded per-walk buffer; the split must be
+    invisible (global Philox counters, per-point reduction)."""
+    s = sc.cfg4()
+    solver = s.make_solver()
+    pts, W = s.points[:37].contiguous(), 300
+    one = solver.solve_raw(pts, W, s.max_steps, s.eps, seed=6, want_walk_vals=True, want_block_stats=True, n_trace=37 * W, trace_cap=4)
+    monkeypatch.setenv("WOST_MAX_WALK_VALS", str(5 * W))               # 5 points per pass -> 8 passes
+    many = solver.solve_raw(pts, W, s.max_steps, s.eps, seed=6, want_walk_vals=True, want_block_stats=True, n_trace=37 * W, trace_cap=4)
+    for k in ("mean", "m2", "walk_vals", "block_stats", "trace_len"):
+        assert np.array_equal(one[k], many[k]), k
+    assert np.array_equal(bits(np.nan_to_num(one["trace"], nan=-1)), bits(np.nan_to_num(many["trace"], nan=-1)))
+    assert int(one["steps"][0]) == int(many["steps"][0])
+    dev = solver.solve_raw(pts.cuda(), W, s.max_steps, s.eps, seed=6, want_walk_vals=True, device_outputs=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["walk_vals"].cpu().numpy(), one["walk_vals"])
