@@ -62,7 +62,7 @@ class DCRSurvey:
         self.solver = WostSolver_2D(dirichletBoundary, None, neumannBoundary, source=None, sigma=None, alpha=conductivity)
         self._fields = [s.field(self.sink_sign) for s in self.sources]
 
-    def run(self, nWalks: int = 1000, maxSteps: int = 500, eps: float = 0.9, seed: int | None = None) -> dict:
+    def run(self, nWalks: int = 1000, maxSteps: int = 500, eps: float = 0.9, seed: int | None = None, streams: int = 8) -> dict:
         """Potentials at every electrode for every source.  Returns
         ``potentials`` (S, E) float64, ``stderr`` (S, E), ``dV`` (S, R) = V_M - V_N per receiver dipole, ``steps``.
         With an initialised ``torch.distributed`` group the sources are dealt round-robin to the ranks and the
@@ -80,11 +80,25 @@ class DCRSurvey:
         S, E = len(self.sources), self.electrodes.shape[0]
         pot, m2 = np.zeros((S, E)), np.zeros((S, E))
         steps = 0
-        for s in range(rank, S, world):
+        # One kernel launch per source over all electrodes.  A launch of a few electrodes does not fill the GPU (the
+        # persistent grid is sized to the work), so sources are issued round-robin on several streams with
+        # device-resident results and collected once at the end.
+        mine = list(range(rank, S, world))
+        n_streams = max(1, min(int(streams), len(mine)))
+        pool = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else [torch.cuda.current_stream()]
+        el_dev = self.electrodes.cuda()
+        pending = []
+        for i, s in enumerate(mine):
             self.solver.setSourceTerm(self._fields[s])
-            # the source index goes into the Philox key, so every source walks its own paths
-            r = self.solver.solve_raw(self.electrodes, nWalks, maxSteps, eps, seed=(seed + 0x9E3779B97F4A7C15 * (s + 1)) % (1 << 64))
-            pot[s], m2[s] = r["mean"], r["m2"]
+            with torch.cuda.stream(pool[i % n_streams]):
+                # the source index goes into the Philox key, so every source walks its own paths
+                r = self.solver.solve_raw(el_dev, nWalks, maxSteps, eps, seed=(seed + 0x9E3779B97F4A7C15 * (s + 1)) % (1 << 64),
+                                          device_outputs=True)
+            pending.append((s, r))
+        for st in pool:
+            st.synchronize()
+        for s, r in pending:
+            pot[s], m2[s] = r["mean"].cpu().numpy(), r["m2"].cpu().numpy()
             steps += int(r["steps"][0])
         if world > 1:
             dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
