@@ -588,9 +588,7 @@ static std::vector<float4> build_bvh(const float* xy, int nvtx, float inflate, i
     }
     for (int i = leaves - 1; i >= 1; --i) {
         const float4 a = nodes[2 * i], b = nodes[2 * i + 1];
-        const bool ea = a.x > a.z, eb = b.x > b.z;                       // never true for real boxes; empties are points
         const bool a_empty = a.x == 3e18f, b_empty = b.x == 3e18f;
-        (void)ea; (void)eb;
         if (a_empty && b_empty) nodes[i] = empty;
         else if (b_empty) nodes[i] = a;
         else if (a_empty) nodes[i] = b;
