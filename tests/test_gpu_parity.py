@@ -573,3 +573,69 @@ def test_edge_inputs_match_oracle():
     assert one["mean"].shape == (1,) and np.isfinite(one["mean"][0])
     est = solver.solve(pts[0], nWalks=16, seed=1)                        # a single (2,) point like the reference's per-point loop
     assert est.shape == (1, 1)
+
+
+def test_reference_script_callables_give_the_scenario_results():
+    """Plain callables exactly as in tests/testWostVariableCoefficients.py and tests/testGeophysicalScenario.py are traced
+    into the same device fields as the hand-written scenarios: same sigma_bar / sigma' mode and, with
+    the same Philox key, the same estimates."""
+    from dcrmontecarlo_b200.utils import torch_smooth_circle
+    import warnings
+
+    def diffusion_coefficient(point):
+        x, y = point[0], point[1]
+        return torch.tensor(0.5 + 1.5 * torch.exp(-2.0 * (x**2 + y**2)))
+
+    def absorption_coefficient(point):
+        x, y = point[0], point[1]
+        return torch.tensor(0.3 + 0.7 * (1 + torch.sin(2*np.pi*x) * torch.cos(2*np.pi*y)))
+
+    def dirichlet_bc(point):
+        x, y = point[0], point[1]
+        return float(torch.sin(np.pi * x) * torch.sin(np.pi * y))
+
+    def source_term(point):
+        x, y = point[0], point[1]
+        r_squared = x**2 + y**2
+        if r_squared > 1.5**2:
+            return 0.0
+        return float(torch.exp(-r_squared) * torch.sin(np.pi * x) * torch.cos(np.pi * y))
+
+    s4 = sc.cfg4()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plain = WostSolver_2D(PolyLinesSimple(s4.dirichlet), None, PolyLinesSimple(s4.neumann), sigma=absorption_coefficient,
+                              alpha=diffusion_coefficient, source=source_term)
+        plain.setBoundaryConditions(dirichlet_bc)
+        ref = s4.make_solver()
+        assert plain.sp_mode == nat.SP_RATIO == ref.sp_mode                 # autograd fails on torch.tensor(...) like in the reference
+        assert plain.sigma_bar == pytest.approx(ref.sigma_bar, rel=1e-6)
+        pts = s4.points[::20].contiguous()
+        a = plain.solve_raw(pts, 4096, s4.max_steps, s4.eps, seed=3)
+        b = ref.solve_raw(pts, 4096, s4.max_steps, s4.eps, seed=3)
+    assert np.allclose(a["mean"], b["mean"], rtol=0, atol=3 * np.sqrt(b["m2"] / 4095 / 4096).max() * 0.2 + 1e-4)
+    assert abs(int(a["steps"][0]) - int(b["steps"][0])) <= 0.01 * int(b["steps"][0])
+
+    def dcr_current_source(point):
+        x, y = point[0], point[1]
+        sigma = 0.5
+        norm = 1.0 / (2 * torch.pi * sigma**2)
+        positive_source = norm * torch.exp(-((x + 10.0)**2 + y**2) / (2 * sigma**2))
+        negative_sink = -norm * torch.exp(-((x - 10.0)**2 + y**2) / (2 * sigma**2))
+        return float(positive_source - negative_sink)
+
+    def conductivity_field(point):
+        background_conductivity = 1e2
+        anomaly1 = (1e1 - background_conductivity) * torch_smooth_circle(point, torch.tensor([-20, -30]), 10)
+        anomaly2 = (1e3 - background_conductivity) * torch_smooth_circle(point, torch.tensor([25, -40]), 10)
+        return background_conductivity + anomaly1 + anomaly2
+
+    s5 = sc.cfg5()
+    plain5 = WostSolver_2D(dirichletBoundary=PolyLinesSimple(s5.dirichlet), dirichletBoundaryFunction=lambda p: 0.0,
+                           neumannBoundary=PolyLinesSimple(s5.neumann), source=dcr_current_source, alpha=conductivity_field, sigma=None)
+    ref5 = s5.make_solver()
+    assert plain5.sigma_bar == ref5.sigma_bar == 10.0 and plain5.sp_mode == nat.SP_FULL
+    a = plain5.solve_raw(s5.points, 8192, s5.max_steps, s5.eps, seed=4)
+    b = ref5.solve_raw(s5.points, 8192, s5.max_steps, s5.eps, seed=4)
+    assert int(a["steps"][0]) == int(b["steps"][0])                         # same geometry, same stream: same walks
+    assert np.allclose(a["mean"], b["mean"], rtol=1e-4, atol=1e-9)
