@@ -42,6 +42,7 @@ struct wost_scene {
     float4* dbvh = nullptr; int dbvh_leaves = 0;      // implicit BVH over the Dirichlet segments (large polylines only)
     float4* nbvh = nullptr; int nbvh_leaves = 0;      // same for the Neumann segments
     float4* ncones = nullptr;                          // silhouette cones of the Neumann hierarchy
+    float4* nwide_boxes = nullptr; float4* nwide_cones = nullptr; WideBvh nwide{};   // 32-wide hierarchy (cooperative queries)
     float bvh_slack = 0.f;                             // ray/box slack (1e-4 of the scene scale)
     int neu_closed = 0;                                // first Neumann vertex == last
     float phys_nudge = 0.f;                            // 1e-5 of the scene scale
@@ -74,6 +75,7 @@ struct WalkArgs {
     float ndisc_x, ndisc_y, ndisc_r, ndisc_r2;   // disc enclosing the Neumann polyline (inflated), for culling
     int sil_coop_max, ray_coop_max;        // answer a query cooperatively when at most this many lanes need it
     Bvh dbvh, nbvh; float bvh_slack;       // hierarchies for large polylines (nodes == nullptr: brute force)
+    WideBvh nwide; int wide_coop_max;      // 32-wide Neumann hierarchy: cooperative queries when few lanes need one
     int neu_closed; float phys_nudge;      // physical mode: closed Neumann loop?  pull-back of a reflected walker
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
@@ -84,7 +86,8 @@ struct WalkArgs {
 // consecutive walk indices per global atomic and deal them out with ballot/popc.
 //
 // The loop body restates solvers/WoStSolver.py:206-298 of the reference, quirks included.
-template <bool NEU, bool SRC, bool DELTA, bool TRACE, bool PHYS>
+// BIG: the scene has hierarchies (large polylines); small scenes get a kernel without any traversal code.
+template <bool NEU, bool SRC, bool DELTA, bool TRACE, bool PHYS, bool BIG>
 __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
     extern __shared__ float4 smem[];
     const float4* dseg = a.dseg; const float4* nseg = a.nseg;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         // physical:  the distance at the current position decides, and g is read at the closest boundary point.
         int dir_arg = -1;
         if (PHYS && active)
-            dD = a.dbvh.nodes ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, &dir_arg) : dirichlet_distance(dseg, a.n_dseg, x, y, &dir_arg);
+            dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, &dir_arg) : dirichlet_distance(dseg, a.n_dseg, x, y, &dir_arg);
         const bool stepping = active && steps < a.max_steps && dD > a.eps;
         if (active && !stepping) {
             // terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7)
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         float gap = 0.0f;
         if (stepping) {
             if (!PHYS)
-                dD = a.dbvh.nodes ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, nullptr)
+                dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, nullptr)
                                   : dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);      // :208
             uint32_t w0;
             if (PHYS) {
@@ -223,9 +226,18 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             const bool small = a.n_nseg <= 32;                                          // warp-uniform
             float dN2 = CUDART_INF_F;                                                   // squared; rooted once below
             unsigned need = __ballot_sync(FULL, want_sil);                              // silhouette distance (:211)
-            if (a.nbvh.nodes) {
-                // large polyline: per-lane descent; only vertices closer than dDirichlet can change r (:212)
-                if (want_sil) dN2 = bvh_silhouette_distance_sq(a.nseg, a.n_nseg, a.nbvh, x, y, TRACE ? CUDART_INF_F : dD * dD * 1.000001f);
+            if (BIG && a.nbvh.nodes) {
+                // large polyline; only vertices closer than dDirichlet can change r (:212).  Few lanes: one warp-cooperative
+                // descent of the 32-wide tree per query; many lanes: every lane descends the binary tree itself.
+                const float bound = TRACE ? CUDART_INF_F : dD * dD * 1.000001f;
+                if (a.nwide.boxes && __popc(need) <= a.wide_coop_max) {
+                    while (need) {
+                        const int src = __ffs(need) - 1; need &= need - 1u;
+                        const float q = wide_silhouette_distance_sq(a.nseg, a.n_nseg, a.nwide, __shfl_sync(FULL, x, src), __shfl_sync(FULL, y, src),
+                                                                    __shfl_sync(FULL, bound, src), lane);
+                        dN2 = lane == src ? q : dN2;
+                    }
+                } else if (want_sil) dN2 = bvh_silhouette_distance_sq(a.nseg, a.n_nseg, a.nbvh, x, y, bound);
             } else if (__popc(need) > a.sil_coop_max) {
                 if (want_sil) dN2 = silhouette_distance_sq(nseg, a.n_nseg, x, y);
             } else {
@@ -240,8 +252,16 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             if (PHYS && a.neu_closed && want_sil) dN2 = fminf(dN2, closing_vertex_silhouette_sq(a.nseg, a.n_nseg, x, y));
             dN = sqrtf(dN2);
             need = __ballot_sync(FULL, want_ray);                                       // ray vs polyline (:162-178)
-            if (a.nbvh.nodes) {
-                if (want_ray) bvh_ray_cast<PHYS>(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, ox, oy, ex, ey, best_s, best_k);
+            if (BIG && a.nbvh.nodes) {
+                if (a.nwide.boxes && __popc(need) <= a.wide_coop_max) {
+                    while (need) {
+                        const int src = __ffs(need) - 1; need &= need - 1u;
+                        float cs; int ck;
+                        wide_ray_cast<PHYS>(a.nseg, a.n_nseg, a.nwide, a.bvh_slack, __shfl_sync(FULL, ox, src), __shfl_sync(FULL, oy, src),
+                                            __shfl_sync(FULL, ex, src), __shfl_sync(FULL, ey, src), lane, cs, ck);
+                        best_s = lane == src ? cs : best_s; best_k = lane == src ? ck : best_k;
+                    }
+                } else if (want_ray) bvh_ray_cast<PHYS>(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, ox, oy, ex, ey, best_s, best_k);
             } else if (__popc(need) > a.ray_coop_max) {
                 if (want_ray) ray_cast<PHYS>(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
             } else {
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 bool vis = true;
                 if (NEU && gap <= rho && ray_may_hit_disc(x, y, c2, s2, a.ndisc_x, a.ndisc_y, a.ndisc_r2)) {
                     float vs; int vk;
-                    if (a.nbvh.nodes) bvh_ray_cast<true>(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, x, y, c2, s2, vs, vk);
+                    if (BIG && a.nbvh.nodes) bvh_ray_cast<true>(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, x, y, c2, s2, vs, vk);
                     else ray_cast<true>(nseg, a.n_nseg, x, y, c2, s2, vs, vk);
                     vis = vk < 0 || vs > rho;
                 }
@@ -637,6 +657,72 @@ static std::vector<float4> build_cones(const float* xy, int nvtx, const std::vec
     return out;
 }
 
+// 32-wide hierarchy over the index order (see wost_device.cuh): level 0 = blocks of 32 segments, level l+1 groups 32
+// level-l nodes, until at most 32 nodes remain.  Returns boxes and cones of all levels concatenated.
+static void build_wide(const float* xy, int nvtx, float inflate, std::vector<float4>& boxes, std::vector<float4>& cones, WideBvh& w) {
+    const int nseg = nvtx - 1;
+    struct Cone { double ax, ay, h; bool empty; };
+    auto merge = [](const Cone& a, const Cone& b) {
+        if (a.empty) return b;
+        if (b.empty) return a;
+        double sx = a.ax + b.ax, sy = a.ay + b.ay, n = std::sqrt(sx * sx + sy * sy);
+        Cone r{1.0, 0.0, M_PI, false};
+        if (n < 1e-9) return r;
+        r.ax = sx / n; r.ay = sy / n;
+        const double da = std::acos(std::fmax(-1.0, std::fmin(1.0, r.ax * a.ax + r.ay * a.ay)));
+        const double db = std::acos(std::fmax(-1.0, std::fmin(1.0, r.ax * b.ax + r.ay * b.ay)));
+        r.h = std::fmin(M_PI, std::fmax(da + a.h, db + b.h));
+        return r;
+    };
+    struct Node { double xmin, ymin, xmax, ymax; Cone c; };
+    std::vector<std::vector<Node>> levels;
+    {   // level 0
+        const int nb = (nseg + 31) / 32;
+        std::vector<Node> L(nb);
+        for (int b = 0; b < nb; ++b) {
+            const int s0 = b * 32, s1 = std::min(s0 + 32, nseg);
+            Node nd{1e300, 1e300, -1e300, -1e300, Cone{1, 0, 0, true}};
+            for (int v = s0; v <= s1; ++v) {
+                nd.xmin = std::fmin(nd.xmin, xy[2 * v]); nd.xmax = std::fmax(nd.xmax, xy[2 * v]);
+                nd.ymin = std::fmin(nd.ymin, xy[2 * v + 1]); nd.ymax = std::fmax(nd.ymax, xy[2 * v + 1]);
+            }
+            for (int k = std::max(s0 - 1, 0); k < s1; ++k) {             // vertex j's test involves segments j-1 and j
+                const double ux = (double)xy[2 * k + 2] - xy[2 * k], uy = (double)xy[2 * k + 3] - xy[2 * k + 1], n = std::sqrt(ux * ux + uy * uy);
+                nd.c = merge(nd.c, Cone{ux / n, uy / n, 0.0, false});
+            }
+            L[b] = nd;
+        }
+        levels.push_back(L);
+    }
+    while ((int)levels.back().size() > 32 && (int)levels.size() < WOST_WIDE_MAX_LEVELS) {
+        const std::vector<Node>& P = levels.back();
+        std::vector<Node> L((P.size() + 31) / 32);
+        for (size_t g = 0; g < L.size(); ++g) {
+            Node nd = P[g * 32];
+            for (size_t k = g * 32 + 1; k < std::min(P.size(), g * 32 + 32); ++k) {
+                nd.xmin = std::fmin(nd.xmin, P[k].xmin); nd.xmax = std::fmax(nd.xmax, P[k].xmax);
+                nd.ymin = std::fmin(nd.ymin, P[k].ymin); nd.ymax = std::fmax(nd.ymax, P[k].ymax);
+                nd.c = merge(nd.c, P[k].c);
+            }
+            L[g] = nd;
+        }
+        levels.push_back(L);
+    }
+    boxes.clear(); cones.clear();
+    w.n_levels = (int)levels.size();
+    for (int l = 0; l < w.n_levels; ++l) {
+        w.off[l] = (int)boxes.size(); w.cnt[l] = (int)levels[l].size();
+        for (const Node& nd : levels[l]) {
+            const float4 b = make_float4((float)nd.xmin - inflate, (float)nd.ymin - inflate, (float)nd.xmax + inflate, (float)nd.ymax + inflate);
+            const double hx = 0.5 * ((double)b.z - b.x), hy = 0.5 * ((double)b.w - b.y);
+            const double R = std::sqrt(hx * hx + hy * hy) * 1.0001;
+            const bool usable = !nd.c.empty && nd.c.h < 0.5 * M_PI - 1e-3;
+            boxes.push_back(b);
+            cones.push_back(make_float4((float)nd.c.ax, (float)nd.c.ay, usable ? (float)std::sin(nd.c.h + 1e-4) : 2.0f, (float)R));
+        }
+    }
+}
+
 static int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return v ? std::atoi(v) : dflt;
@@ -645,26 +731,26 @@ static int env_int(const char* name, int dflt) {
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 typedef void (*walk_kernel_t)(const WalkArgs);
-template <bool TRACE>
+template <bool TRACE, bool BIG>
 static walk_kernel_t pick_kernel(bool neu, bool src, bool delta, bool phys) {
     const int m = (neu ? 4 : 0) | (src ? 2 : 0) | (delta ? 1 : 0);
     if (phys) {                                        // physical mode: constant coefficients only (checked by the caller)
         switch (m) {
-            case 0: return walk_kernel<false, false, false, TRACE, true>;
-            case 2: return walk_kernel<false, true, false, TRACE, true>;
-            case 4: return walk_kernel<true, false, false, TRACE, true>;
-            default: return walk_kernel<true, true, false, TRACE, true>;
+            case 0: return walk_kernel<false, false, false, TRACE, true, BIG>;
+            case 2: return walk_kernel<false, true, false, TRACE, true, BIG>;
+            case 4: return walk_kernel<true, false, false, TRACE, true, BIG>;
+            default: return walk_kernel<true, true, false, TRACE, true, BIG>;
         }
     }
     switch (m) {
-        case 0: return walk_kernel<false, false, false, TRACE, false>;
-        case 1: return walk_kernel<false, false, true, TRACE, false>;
-        case 2: return walk_kernel<false, true, false, TRACE, false>;
-        case 3: return walk_kernel<false, true, true, TRACE, false>;
-        case 4: return walk_kernel<true, false, false, TRACE, false>;
-        case 5: return walk_kernel<true, false, true, TRACE, false>;
-        case 6: return walk_kernel<true, true, false, TRACE, false>;
-        default: return walk_kernel<true, true, true, TRACE, false>;
+        case 0: return walk_kernel<false, false, false, TRACE, false, BIG>;
+        case 1: return walk_kernel<false, false, true, TRACE, false, BIG>;
+        case 2: return walk_kernel<false, true, false, TRACE, false, BIG>;
+        case 3: return walk_kernel<false, true, true, TRACE, false, BIG>;
+        case 4: return walk_kernel<true, false, false, TRACE, false, BIG>;
+        case 5: return walk_kernel<true, false, true, TRACE, false, BIG>;
+        case 6: return walk_kernel<true, true, false, TRACE, false, BIG>;
+        default: return walk_kernel<true, true, true, TRACE, false, BIG>;
     }
 }
 
@@ -766,9 +852,18 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
             const std::vector<float4> cones = build_cones(nxy, nn, nodes, s->nbvh_leaves);
             if (be == cudaSuccess) be = cudaMalloc((void**)&s->ncones, cones.size() * sizeof(float4));
             if (be == cudaSuccess) be = cudaMemcpy(s->ncones, cones.data(), cones.size() * sizeof(float4), cudaMemcpyHostToDevice);
+            std::vector<float4> wb, wc;
+            build_wide(nxy, nn, inflate, wb, wc, s->nwide);
+            if ((int)wb.size() > 0 && s->nwide.cnt[s->nwide.n_levels - 1] <= 32) {
+                if (be == cudaSuccess) be = cudaMalloc((void**)&s->nwide_boxes, wb.size() * sizeof(float4));
+                if (be == cudaSuccess) be = cudaMemcpy(s->nwide_boxes, wb.data(), wb.size() * sizeof(float4), cudaMemcpyHostToDevice);
+                if (be == cudaSuccess) be = cudaMalloc((void**)&s->nwide_cones, wc.size() * sizeof(float4));
+                if (be == cudaSuccess) be = cudaMemcpy(s->nwide_cones, wc.data(), wc.size() * sizeof(float4), cudaMemcpyHostToDevice);
+                s->nwide.boxes = s->nwide_boxes; s->nwide.cones = s->nwide_cones;
+            }
         }
         if (be != cudaSuccess) {
-            cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones); delete s;
+            cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones); cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones); delete s;
             return fail(WOST_ERR_CUDA, std::string("BVH upload: ") + cudaGetErrorString(be));
         }
     }
@@ -781,6 +876,7 @@ int wost_scene_destroy(wost_scene_t* s) {
     if (!s) return WOST_OK;
     DeviceGuard g(s->device);
     cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones);
+    cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones);
     delete s;
     return WOST_OK;
 }
@@ -963,6 +1059,7 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
         if (a.ray_coop_max > 32) a.ray_coop_max = 32;
     }
     a.dbvh.nodes = scene->dbvh; a.dbvh.n_leaves = scene->dbvh_leaves; a.nbvh.nodes = scene->nbvh; a.nbvh.cones = scene->ncones; a.nbvh.n_leaves = scene->nbvh_leaves;
+    a.nwide = scene->nwide; a.wide_coop_max = env_int("WOST_WIDE_COOP_MAX", 20);
     a.bvh_slack = scene->bvh_slack; a.neu_closed = scene->neu_closed; a.phys_nudge = scene->phys_nudge;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
@@ -971,7 +1068,9 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     a.stage_smem = seg_bytes <= 96 * 1024 ? 1 : 0;
     const size_t smem = a.stage_smem ? seg_bytes : 0;
     const bool phys = P->compat_mode == WOST_COMPAT_PHYSICAL;
-    walk_kernel_t kern = trace ? pick_kernel<true>(neu, src, delta, phys) : pick_kernel<false>(neu, src, delta, phys);
+    const bool big = scene->dbvh != nullptr || scene->nbvh != nullptr;
+    walk_kernel_t kern = big ? (trace ? pick_kernel<true, true>(neu, src, delta, phys) : pick_kernel<false, true>(neu, src, delta, phys))
+                             : (trace ? pick_kernel<true, false>(neu, src, delta, phys) : pick_kernel<false, false>(neu, src, delta, phys));
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, threads, smem));

@@ -111,8 +111,8 @@ def main():
         ("cfg1a", sc.cfg1a(), N, 256), ("cfg1b", sc.cfg1b(), N, 64), ("cfg2", sc.cfg2(), N, 256), ("cfg3", sc.cfg3(), N, 256),
         ("cfg4", sc.cfg4(), N, 64), ("cfg5_9e", sc.cfg5(9), 9, 32768 if not a.quick else 8192),
         ("cfg5_175e", sc.cfg5(175), 175, 4096 if not a.quick else 1024),
-        ("scale_32", sc.scale_scene(32, N, 64), None, 64), ("scale_1024", sc.scale_scene(1024, N // 4, 16), None, 16),
-        ("scale_16384", sc.scale_scene(16384, 4096, 4), None, 4),
+        ("scale_32", sc.scale_scene(32, N, 64), None, 64), ("scale_1024", sc.scale_scene(1024, N, 16), None, 16),
+        ("scale_16384", sc.scale_scene(16384, N, 16), None, 16),
     ]
     res = {"fp32_peak_tflops": peak_tf, "fp32_peak_effective_sm_mhz": mhz, "configs": {}}
     for name, s, n_pts, walks in plan:
