@@ -43,6 +43,7 @@ struct wost_scene {
     float4* nbvh = nullptr; int nbvh_leaves = 0;      // same for the Neumann segments
     float4* ncones = nullptr;                          // silhouette cones of the Neumann hierarchy
     float4* nwide_boxes = nullptr; float4* nwide_cones = nullptr; WideBvh nwide{};   // 32-wide hierarchy (cooperative queries)
+    float4* dwide_boxes = nullptr; WideBvh dwide{};                                   // same for the Dirichlet polyline (boxes only)
     float bvh_slack = 0.f;                             // ray/box slack (1e-4 of the scene scale)
     int neu_closed = 0;                                // first Neumann vertex == last
     float phys_nudge = 0.f;                            // 1e-5 of the scene scale
@@ -76,6 +77,7 @@ struct WalkArgs {
     int sil_coop_max, ray_coop_max;        // answer a query cooperatively when at most this many lanes need it
     Bvh dbvh, nbvh; float bvh_slack;       // hierarchies for large polylines (nodes == nullptr: brute force)
     WideBvh nwide; int wide_coop_max;      // 32-wide Neumann hierarchy: cooperative queries when few lanes need one
+    WideBvh dwide;                         // 32-wide Dirichlet hierarchy: the distance query, one warp per query
     int neu_closed; float phys_nudge;      // physical mode: closed Neumann loop?  pull-back of a reflected walker
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
@@ -169,12 +171,22 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             active = false;
         }
 
+        // very large Dirichlet polylines: the distance query of every stepping lane, one warp-cooperative descent each
+        if (BIG && !PHYS && a.dwide.boxes) {
+            unsigned need = __ballot_sync(FULL, stepping);
+            while (need) {
+                const int src = __ffs(need) - 1; need &= need - 1u;
+                const float q = wide_dirichlet_distance_sq(a.dseg, a.n_dseg, a.dwide, __shfl_sync(FULL, x, src), __shfl_sync(FULL, y, src), lane, nullptr);
+                if (lane == src) dD = sqrtf(q);
+            }
+        }
+
         // ---- phase A: Dirichlet distance, direction --------------------------------------------------------------
         float dN = CUDART_INF_F, r = 0.f, dx = 0.f, dy = 0.f, ex = 0.f, ey = 0.f, ox = 0.f, oy = 0.f;
         bool want_ray = false, want_sil = false;
         float gap = 0.0f;
         if (stepping) {
-            if (!PHYS)
+            if (!PHYS && !(BIG && a.dwide.boxes))
                 dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, nullptr)
                                   : dirichlet_distance(dseg, a.n_dseg, x, y, nullptr);      // :208
             uint32_t w0;
@@ -844,6 +856,13 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
             const std::vector<float4> nodes = build_bvh(dxy, nd, inflate, &s->dbvh_leaves);
             be = cudaMalloc((void**)&s->dbvh, nodes.size() * sizeof(float4));
             if (be == cudaSuccess) be = cudaMemcpy(s->dbvh, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice);
+            std::vector<float4> wb, wc;
+            build_wide(dxy, nd, inflate, wb, wc, s->dwide);
+            if (s->n_dseg >= env_int("WOST_WIDE_MIN_DIRICHLET", 512) && s->dwide.cnt[s->dwide.n_levels - 1] <= 32) {
+                if (be == cudaSuccess) be = cudaMalloc((void**)&s->dwide_boxes, wb.size() * sizeof(float4));
+                if (be == cudaSuccess) be = cudaMemcpy(s->dwide_boxes, wb.data(), wb.size() * sizeof(float4), cudaMemcpyHostToDevice);
+                s->dwide.boxes = s->dwide_boxes;
+            }
         }
         if (be == cudaSuccess && s->n_nseg >= env_int("WOST_BVH_MIN_NEUMANN", 192)) {
             const std::vector<float4> nodes = build_bvh(nxy, nn, inflate, &s->nbvh_leaves);
@@ -863,7 +882,7 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
             }
         }
         if (be != cudaSuccess) {
-            cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones); cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones); delete s;
+            cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones); cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones); cudaFree(s->dwide_boxes); delete s;
             return fail(WOST_ERR_CUDA, std::string("BVH upload: ") + cudaGetErrorString(be));
         }
     }
@@ -876,7 +895,7 @@ int wost_scene_destroy(wost_scene_t* s) {
     if (!s) return WOST_OK;
     DeviceGuard g(s->device);
     cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones);
-    cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones);
+    cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones); cudaFree(s->dwide_boxes);
     delete s;
     return WOST_OK;
 }
@@ -1059,7 +1078,7 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
         if (a.ray_coop_max > 32) a.ray_coop_max = 32;
     }
     a.dbvh.nodes = scene->dbvh; a.dbvh.n_leaves = scene->dbvh_leaves; a.nbvh.nodes = scene->nbvh; a.nbvh.cones = scene->ncones; a.nbvh.n_leaves = scene->nbvh_leaves;
-    a.nwide = scene->nwide; a.wide_coop_max = env_int("WOST_WIDE_COOP_MAX", 20);
+    a.dwide = scene->dwide; a.nwide = scene->nwide; a.wide_coop_max = env_int("WOST_WIDE_COOP_MAX", 20);
     a.bvh_slack = scene->bvh_slack; a.neu_closed = scene->neu_closed; a.phys_nudge = scene->phys_nudge;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
