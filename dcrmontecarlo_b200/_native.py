@@ -218,14 +218,14 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
         blk = mk((P, nblk, 2), torch.float64) if want_block_stats else None
         vals = mk((P, n_walks), torch.float32) if want_walk_vals else None
         steps = mk((1,), torch.int64)
-        trace = mk((n_trace, trace_cap, 4), torch.float32) if n_trace else None
+        trace = mk((n_trace, trace_cap + 1, 8), torch.float32) if n_trace else None
         tlen = mk((n_trace,), torch.int32) if n_trace else None
     else:
         mean, m2 = np.empty(P, np.float64), np.empty(P, np.float64)
         blk = np.empty((P, nblk, 2), np.float64) if want_block_stats else None
         vals = np.empty((P, n_walks), np.float32) if want_walk_vals else None
         steps = np.zeros(1, np.uint64)
-        trace = np.empty((n_trace, trace_cap, 4), np.float32) if n_trace else None
+        trace = np.empty((n_trace, trace_cap + 1, 8), np.float32) if n_trace else None
         tlen = np.empty(n_trace, np.int32) if n_trace else None
     check(lib().wost_solve(scene.handle, C.byref(fields), C.byref(prm), ptr(p), P, ptr(mean), ptr(m2), ptr(blk), ptr(vals),
                            ptr(steps), int(n_trace), int(trace_cap), ptr(trace), ptr(tlen), current_stream(dev)))

@@ -166,7 +166,14 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, gx_, gy_) : field_eval_inl(a.F.g, gx_, gy_);
             if (DELTA) bc = bc * atten;
             a.walk_vals[id] = total_v + bc;
-            if (TRACE) { if ((long long)id < a.n_trace) a.trace_len[id] = min(steps, a.trace_cap); }
+            if (TRACE) {
+                if ((long long)id < a.n_trace) {                          // terminal row: where g was read, what it contributed
+                    const int len = min(steps, a.trace_cap);
+                    a.trace_len[id] = len;
+                    float4* t = reinterpret_cast<float4*>(a.trace) + ((size_t)id * (a.trace_cap + 1) + len) * 2;
+                    t[0] = make_float4(gx_, gy_, bc, total_v + bc); t[1] = make_float4((float)steps, 0.0f, 0.0f, 1.0f);
+                }
+            }
             steps_acc += (unsigned long long)steps;
             active = false;
         }
@@ -309,7 +316,12 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                     else ray_cast<true>(nseg, a.n_nseg, x, y, c2, s2, vs, vk);
                     vis = vk < 0 || vs > rho;
                 }
-                if (vis) total_v += field_eval_inl(a.F.f, x + rho * c2, y + rho * s2) * (r * r / 4.0f);
+                const float pc = vis ? field_eval_inl(a.F.f, x + rho * c2, y + rho * s2) * (r * r / 4.0f) : 0.0f;
+                total_v += pc;
+                if (TRACE) {
+                    if ((long long)id < a.n_trace && steps < a.trace_cap)
+                        reinterpret_cast<float4*>(a.trace)[((size_t)id * (a.trace_cap + 1) + steps) * 2 + 1] = make_float4(x + rho * c2, y + rho * s2, pc, 0.0f);
+                }
             }
             if (NEU) {
                 if (PHYS) {
@@ -334,8 +346,8 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             }
             if (TRACE) {
                 if ((long long)id < a.n_trace && steps < a.trace_cap) {
-                    float4* t = reinterpret_cast<float4*>(a.trace) + (size_t)id * a.trace_cap + steps;
-                    *t = make_float4(x, y, dD, dN);
+                    float4* t = reinterpret_cast<float4*>(a.trace) + ((size_t)id * (a.trace_cap + 1) + steps) * 2;
+                    t[0] = make_float4(x, y, dD, dN);
                 }
             }
 
@@ -369,6 +381,10 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                         contrib = field_eval_inl(a.F.f, sx, sy) * (r * r / 4.0f);       // :256
                 }
                 if (SRC) total_v += contrib;                                            // :258
+                if (TRACE && SRC) {                                                     // :261-267 history: the source sample
+                    if ((long long)id < a.n_trace && steps < a.trace_cap)
+                        reinterpret_cast<float4*>(a.trace)[((size_t)id * (a.trace_cap + 1) + steps) * 2 + 1] = make_float4(sx, sy, contrib, 0.0f);
+                }
             }
             if (DELTA) {                                                                // :271-284
                 // alpha(current_point) is the value computed when the walker arrived here (same function, same point)
@@ -1033,7 +1049,7 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     if ((rc = s_icdf.init(delta ? P->screened_icdf : nullptr, delta ? P->icdf_len : 0, false, st))) return rc;
     if ((rc = s_mean.init(out_mean, n_pts, true, st)) || (rc = s_m2.init(out_m2, n_pts, true, st)) ||
         (rc = s_blk.init(out_block_stats, 2 * n_pts * nblk, true, st)) || (rc = s_steps.init(out_steps, 1, true, st)) ||
-        (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * trace_cap * 4 : 0, true, st)) ||
+        (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * (trace_cap + 1) * 8 : 0, true, st)) ||
         (rc = s_tlen.init(out_trace_len, trace ? n_trace : 0, true, st))) return rc;
 
     // scratch: per-walk totals (unless the caller wants them), counters, block statistics
@@ -1052,7 +1068,7 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     double* blk = s_blk.dev; bool blk_temp = false;
     if (!blk) { CU(cudaMallocAsync((void**)&blk, sizeof(double) * 2 * n_pts * nblk, st)); blk_temp = true; }
     if (trace) {
-        CU(cudaMemsetAsync(s_trace.dev, 0xff, sizeof(float) * (size_t)n_trace * trace_cap * 4, st));   // NaN fill
+        CU(cudaMemsetAsync(s_trace.dev, 0xff, sizeof(float) * (size_t)n_trace * (trace_cap + 1) * 8, st));   // NaN fill
         CU(cudaMemsetAsync(s_tlen.dev, 0, sizeof(int32_t) * n_trace, st));
     }
 
@@ -1110,7 +1126,7 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
         if (trace) {                                                    // the first n_trace walks in point-major order
             const long long first = p0 * W;
             a.n_trace = std::max(0ll, std::min((long long)n_trace - first, total));
-            a.trace = s_trace.dev + (size_t)first * trace_cap * 4; a.trace_len = s_tlen.dev + first;
+            a.trace = s_trace.dev + (size_t)first * (trace_cap + 1) * 8; a.trace_len = s_tlen.dev + first;
         }
         if (p0 > 0) CU(cudaMemsetAsync(ctrs, 0, sizeof(unsigned long long), st));   // walk counter only; steps accumulate
         kern<<<(unsigned)grid, threads, smem, st>>>(a);

@@ -300,20 +300,27 @@ class WostSolver_2D:
         return (out, *extras) if extras else out
 
     def _history(self, res, pts, W):
-        """History dictionary in the reference's schema (:335-349) rebuilt from the device trace buffer.  Per-step
-        source contributions are not traced; each walk carries one summary contribution."""
+        """History dictionary in the reference's schema (:335-349) rebuilt from the device trace buffer: per walk the
+        visited points with their cached distances, one 'source' contribution per step (when there is a source term),
+        the final 'boundary' contribution, and the running point total (:308)."""
         hist = {}
         trace, tlen, vals = res["trace"], res["trace_len"], res["walk_vals"]
-        has_neu = self.neumannBoundary is not None
+        has_neu, has_src = self.neumannBoundary is not None, self.source is not None
         for p in range(pts.shape[0]):
             running, walks = 0.0, []
             for w in range(W):
                 flat = p * W + w
-                path = [{"point": torch.tensor(trace[flat, k, :2]), "dirichlet_distance": float(trace[flat, k, 2]),
-                         "neumann_distance": float(trace[flat, k, 3]) if has_neu else None} for k in range(int(tlen[flat]))]
+                n = int(tlen[flat])
+                rows = trace[flat]
+                path = [{"point": torch.tensor(rows[k, :2]), "dirichlet_distance": float(rows[k, 2]),
+                         "neumann_distance": float(rows[k, 3]) if has_neu else None} for k in range(n)]
+                contributions = []
+                if has_src:
+                    contributions += [{"step": k, "type": "source", "point": torch.tensor(rows[k, 4:6]), "contribution": float(rows[k, 6])}
+                                      for k in range(n)]
+                contributions.append({"step": int(rows[n, 4]), "type": "boundary", "point": torch.tensor(rows[n, :2]),
+                                      "contribution": float(rows[n, 2])})
                 running += float(vals[p, w])
-                walks.append({"walk_id": w, "path": path,
-                              "contributions": [{"step": int(tlen[flat]), "type": "walk_total", "point": None, "contribution": float(vals[p, w])}],
-                              "total_contribution": running})
+                walks.append({"walk_id": w, "path": path, "contributions": contributions, "total_contribution": running})
             hist[p] = walks
         return hist

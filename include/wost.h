@@ -149,8 +149,11 @@ int wost_sigma_prime_eval(const wost_fields_t* fields, int32_t sp_mode, const fl
  *                    walk-sharded multi-GPU runs
  *   out_walk_vals[n_pts * n_walks] fp32 per-walk totals
  *   out_steps[1]     total walk steps taken (one step = one pass of the loop at :206)
- *   trace: for the first n_trace walks (point-major flat index) up to trace_cap steps of
- *          (x, y, dDirichlet, dNeumann) and trace_len[n_trace]          (return_history, :198-223) */
+ *   trace (return_history, :198-223,261-267,301-309): for the first n_trace walks (point-major flat index)
+ *          out_trace[n_trace][trace_cap + 1][8] and out_trace_len[n_trace].  Row k < len is step k:
+ *          (x, y, dDirichlet, dNeumann, sample_x, sample_y, source_contribution, 0) — the last four NaN without a
+ *          source; row `len` is the terminal record (x_g, y_g, boundary_contribution, walk_total, steps, 0, 0, 1)
+ *          where (x_g, y_g) is the point the Dirichlet data was read at.  Unused entries are NaN. */
 int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wost_solve_params_t* params,
                const float* pts_xy, int64_t n_pts,
                double* out_mean, double* out_m2, double* out_block_stats, float* out_walk_vals,

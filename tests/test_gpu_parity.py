@@ -166,7 +166,7 @@ def test_walks_match_oracle_per_walk(key):
     lim = float(s.dirichlet.abs().max())
     for i in range(len(n3)):
         # 1e-5 of the coordinate scale (distances are differences of coordinates)
-        assert np.allclose(r["trace"][i, : n3[i]], o["trace"][i, : n3[i]], rtol=1e-5, atol=1e-5 * lim), (key, i)
+        assert np.allclose(r["trace"][i, : n3[i], :4], o["trace"][i, : n3[i]], rtol=1e-5, atol=1e-5 * lim), (key, i)
     same_len = r["trace_len"] == o["trace_len"]
     assert same_len.mean() > 0.9
     dv = np.abs(r["walk_vals"] - o["walk_vals"])
@@ -247,6 +247,21 @@ def test_solve_api_shapes_seeding_and_history():
     assert {"walk_id", "path", "contributions", "total_contribution"} <= set(w0)
     assert torch.allclose(w0["path"][0]["point"], pts[0]) and w0["path"][0]["neumann_distance"] is not None
     assert hist[0][-1]["total_contribution"] / 5 == pytest.approx(est[0, 0].item(), rel=1e-5, abs=1e-6)
+    # Laplace: one 'boundary' contribution, read at the walk's last position (g = x here), equal to the walk total
+    assert [c["type"] for c in w0["contributions"]] == ["boundary"]
+    b = w0["contributions"][0]
+    assert b["step"] == len(w0["path"]) and b["contribution"] == pytest.approx(w0["total_contribution"], rel=1e-6)
+    assert b["contribution"] == pytest.approx(b["point"][0].item(), rel=1e-6, abs=1e-7)
+    # with a source term: one 'source' contribution per step plus the boundary one, summing to the walk total
+    s3 = sc.cfg3()
+    est3, hist3 = s3.make_solver().solve(s3.points[:2], nWalks=4, maxSteps=s3.max_steps, eps=s3.eps, return_history=True, seed=3)
+    for wk in hist3[1]:
+        kinds = [c["type"] for c in wk["contributions"]]
+        assert kinds == ["source"] * len(wk["path"]) + ["boundary"]
+    first = hist3[0][0]
+    assert sum(c["contribution"] for c in first["contributions"]) == pytest.approx(first["total_contribution"], rel=1e-5)
+    assert all(abs(c["contribution"] + c_r2) < 1e-5 or c["contribution"] == 0.0 for c, c_r2 in
+               zip(first["contributions"][:-1], [min(p["dirichlet_distance"], 1e9) ** 2 for p in first["path"]]))   # f = -4: -r^2
     cuda_est = solver.solve(pts.cuda(), nWalks=64, maxSteps=s.max_steps, eps=s.eps, seed=8)
     assert cuda_est.is_cuda and torch.equal(cuda_est.cpu(), solver.solve(pts, nWalks=64, maxSteps=s.max_steps, eps=s.eps, seed=8))
 
@@ -503,7 +518,7 @@ def test_physical_mode_kernel_matches_oracle_and_analytic(key):
                                            walk_vals=True, n_trace=len(s.points) * W, trace_cap=6)
     n3 = np.minimum(np.minimum(r["trace_len"], o["trace_len"]), 3)
     for i in range(len(n3)):
-        assert np.allclose(r["trace"][i, : n3[i]], o["trace"][i, : n3[i]], rtol=1e-5, atol=2e-5), (key, i)
+        assert np.allclose(r["trace"][i, : n3[i], :4], o["trace"][i, : n3[i]], rtol=1e-5, atol=2e-5), (key, i)
     dv = np.abs(r["walk_vals"] - o["walk_vals"])
     assert (dv <= 2e-3 * (1 + np.abs(o["walk_vals"]))).mean() > 0.85, (key, (dv <= 2e-3 * (1 + np.abs(o["walk_vals"]))).mean())
     assert abs(int(r["steps"][0]) - o["steps"]) <= 0.05 * o["steps"]
