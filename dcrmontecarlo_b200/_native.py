@@ -64,6 +64,8 @@ EXPORTS = {
     "wost_solve": (C.c_int, [C.c_void_p, C.POINTER(Fields), C.POINTER(SolveParams), C.c_void_p, C.c_int64,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wost_solve_multi_source": (C.c_int, [C.c_void_p, C.POINTER(Fields), C.POINTER(C.c_void_p), C.c_int32, C.POINTER(SolveParams),
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wost_merge_block_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wost_geom_distance": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wost_geom_silhouette": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -236,6 +238,46 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
         out["walk_vals"] = vals
     if n_trace:
         out["trace"], out["trace_len"] = trace, tlen
+    return out
+
+
+def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int, max_steps: int, eps: float, *,
+                       delta: bool = False, sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0,
+                       point_index_base: int = 0, walk_offset: int = 0, want_block_stats: bool = False,
+                       device_outputs: bool = False, compat: str = "reference"):
+    """One wost_solve_multi_source call: shared walks, one estimate per (source, point).  ``sources`` is a list of
+    DeviceField.  Returns mean / m2 of shape (S, P)."""
+    dev = scene.device
+    if isinstance(pts, torch.Tensor) and pts.is_cuda:
+        p = pts.detach().to(torch.float32).contiguous().reshape(-1, 2)
+    else:
+        p = host_f32(pts).reshape(-1, 2)
+    P, S = int(p.shape[0]), len(sources)
+    nblk = (n_walks + WALK_BLOCK - 1) // WALK_BLOCK
+    prm = SolveParams()
+    prm.n_walks, prm.max_steps, prm.eps = int(n_walks), int(max_steps), float(eps)
+    prm.delta_tracking, prm.sp_mode, prm.sigma_bar = int(bool(delta)), int(sp_mode), float(sigma_bar)
+    icdf_keep = None
+    if delta:
+        icdf_keep = icdf if (isinstance(icdf, torch.Tensor) and icdf.is_cuda) else host_f32(icdf)
+        prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
+    prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
+    prm.compat_mode = COMPAT[compat]
+    handles = (C.c_void_p * S)(*[s.handle for s in sources])
+    if device_outputs:
+        tdev = torch.device("cuda", dev)
+        mean, m2 = torch.empty((S, P), dtype=torch.float64, device=tdev), torch.empty((S, P), dtype=torch.float64, device=tdev)
+        blk = torch.empty((S, P, nblk, 2), dtype=torch.float64, device=tdev) if want_block_stats else None
+        steps = torch.empty((1,), dtype=torch.int64, device=tdev)
+    else:
+        mean, m2 = np.empty((S, P), np.float64), np.empty((S, P), np.float64)
+        blk = np.empty((S, P, nblk, 2), np.float64) if want_block_stats else None
+        steps = np.zeros(1, np.uint64)
+    check(lib().wost_solve_multi_source(scene.handle, C.byref(fields), handles, S, C.byref(prm), ptr(p), P, ptr(mean), ptr(m2),
+                                        ptr(blk), ptr(steps), current_stream(dev)))
+    out = dict(mean=mean, m2=m2, steps=steps, n=n_walks)
+    if want_block_stats:
+        out["block_stats"] = blk
     return out
 
 

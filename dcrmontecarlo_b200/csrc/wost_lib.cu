@@ -79,6 +79,8 @@ struct WalkArgs {
     WideBvh nwide; int wide_coop_max;      // 32-wide Neumann hierarchy: cooperative queries when few lanes need one
     WideBvh dwide;                         // 32-wide Dirichlet hierarchy: the distance query, one warp per query
     int neu_closed; float phys_nudge;      // physical mode: closed Neumann loop?  pull-back of a reflected walker
+    int n_src; const DevField* srcs;       // shared-walk multi-source solve: n_src > 0 source fields (device array); per-walk
+                                           // totals then form rows walk_vals[walk][n_src]
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
 
@@ -165,7 +167,10 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             float bc = 0.0f;
             if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, gx_, gy_) : field_eval_inl(a.F.g, gx_, gy_);
             if (DELTA) bc = bc * atten;
-            a.walk_vals[id] = total_v + bc;
+            if (SRC && a.n_src > 0) {                                     // one total per source: same walk, same boundary term
+                float* row = a.walk_vals + (size_t)id * a.n_src;
+                for (int k = 0; k < a.n_src; ++k) row[k] = row[k] + bc;
+            } else a.walk_vals[id] = total_v + bc;
             if (TRACE) {
                 if ((long long)id < a.n_trace) {                          // terminal row: where g was read, what it contributed
                     const int len = min(steps, a.trace_cap);
@@ -316,8 +321,19 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                     else ray_cast<true>(nseg, a.n_nseg, x, y, c2, s2, vs, vk);
                     vis = vk < 0 || vs > rho;
                 }
-                const float pc = vis ? field_eval_inl(a.F.f, x + rho * c2, y + rho * s2) * (r * r / 4.0f) : 0.0f;
-                total_v += pc;
+                float pc = 0.0f;
+                if (a.n_src > 0) {
+                    if (vis) {
+                        float* row = a.walk_vals + (size_t)id * a.n_src;
+                        for (int k = 0; k < a.n_src; ++k) {
+                            const float ck = field_eval(a.srcs[k], x + rho * c2, y + rho * s2) * (r * r / 4.0f);
+                            if (ck != 0.0f) row[k] = row[k] + ck;
+                        }
+                    }
+                } else {
+                    pc = vis ? field_eval_inl(a.F.f, x + rho * c2, y + rho * s2) * (r * r / 4.0f) : 0.0f;
+                    total_v += pc;
+                }
                 if (TRACE) {
                     if ((long long)id < a.n_trace && steps < a.trace_cap)
                         reinterpret_cast<float4*>(a.trace)[((size_t)id * (a.trace_cap + 1) + steps) * 2 + 1] = make_float4(x + rho * c2, y + rho * s2, pc, 0.0f);
@@ -374,7 +390,18 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 if (norm2(sx - x, sy - y) > norm2(qx - x, qy - y)) {                    // :248-250
                     sx = qx; sy = qy;
                 } else if (SRC) {
-                    if (DELTA) {                                                        // :252-254
+                    if (a.n_src > 0) {
+                        // shared walks: the path does not depend on f, so one walk serves every source; each source
+                        // accumulates exactly the sum a single-source solve would (same expressions, same order)
+                        float* row = a.walk_vals + (size_t)id * a.n_src;
+                        float den = 1.0f;
+                        if (DELTA) { alpha_s = alpha_at(a.F, sx, sy); have_alpha_s = true; den = sqrtf(alpha_s * alpha_x); }
+                        const float w4 = r * r / 4.0f;
+                        for (int k = 0; k < a.n_src; ++k) {
+                            const float fk = field_eval(a.srcs[k], sx, sy);
+                            if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);
+                        }
+                    } else if (DELTA) {                                                 // :252-254
                         alpha_s = alpha_at(a.F, sx, sy); have_alpha_s = true;
                         contrib = (field_eval(a.F.f, sx, sy) * gn / sqrtf(alpha_s * alpha_x)) * atten;
                     } else
@@ -413,15 +440,20 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
 // kernels: deterministic statistics
 // =================================================================================================
 // One warp per (point, block of WOST_WALK_BLOCK walks): two-pass mean / M2 in fp64, fixed summation order.
+// vals[(p * n_walks + w) * stride + blockIdx.y] (stride = number of sources of a shared-walk solve, else 1);
+// stats[((blockIdx.y * n_pts_total + p_off + p) * nblk + b) * 2].
 __global__ void __launch_bounds__(256) block_stats_kernel(const float* __restrict__ vals, long long n_pts, long long n_walks,
-                                                          long long nblk, double* __restrict__ stats) {
+                                                          long long nblk, double* __restrict__ stats, int stride = 1,
+                                                          long long n_pts_total = 0, long long p_off = 0) {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_pts * nblk) return;
     const long long p = warp / nblk, b = warp - p * nblk;
     const long long w0 = b * WOST_WALK_BLOCK;
     const int n = (int)min((long long)WOST_WALK_BLOCK, n_walks - w0);
-    const float* v = vals + p * n_walks + w0;
+    const float* v0 = vals + (p * n_walks + w0) * stride + blockIdx.y;
+    stats += 2 * ((long long)blockIdx.y * n_pts_total + p_off) * nblk;
+    struct Strided { const float* p; int st; __device__ float operator[](int i) const { return p[(long long)i * st]; } } v{v0, stride};
     double s = 0.0;
     for (int i = lane; i < n; i += 32) s += (double)v[i];
 #pragma unroll
@@ -1009,10 +1041,13 @@ int wost_sigma_prime_eval(const wost_fields_t* F, int32_t sp_mode, const float* 
     return WOST_OK;
 }
 
-int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wost_solve_params_t* P,
-               const float* pts_xy, int64_t n_pts,
-               double* out_mean, double* out_m2, double* out_block_stats, float* out_walk_vals, uint64_t* out_steps,
-               int64_t n_trace, int32_t trace_cap, float* out_trace, int32_t* out_trace_len, void* stream) {
+}  // extern "C"
+
+// Shared implementation of wost_solve (n_sources == 0: the source is fields->f) and wost_solve_multi_source.
+static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, const wost_field_t* const* sources, int n_sources,
+                      const wost_solve_params_t* P, const float* pts_xy, int64_t n_pts,
+                      double* out_mean, double* out_m2, double* out_block_stats, float* out_walk_vals, uint64_t* out_steps,
+                      int64_t n_trace, int32_t trace_cap, float* out_trace, int32_t* out_trace_len, void* stream) {
     if (!scene || !P || !pts_xy) return fail(WOST_ERR_INVALID, "scene, params and pts_xy are required");
     if (n_pts < 0 || P->n_walks <= 0 || P->max_steps < 0) return fail(WOST_ERR_INVALID, "n_pts >= 0, n_walks > 0, max_steps >= 0 required");
     if (!(P->eps >= 0.0f)) return fail(WOST_ERR_INVALID, "eps must be >= 0");
@@ -1041,14 +1076,18 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     const long long W = P->n_walks;
     const long long nblk = (W + WOST_WALK_BLOCK - 1) / WOST_WALK_BLOCK;
     const bool trace = n_trace > 0;
-    const bool neu = scene->n_nseg > 0, src = fields && fields->f;
+    const int S = n_sources > 0 ? n_sources : 1;                        // totals per walk
+    const bool neu = scene->n_nseg > 0, src = n_sources > 0 || (fields && fields->f);
+    for (int k = 0; k < n_sources; ++k)
+        if (!sources[k] || sources[k]->device != scene->device) return fail(WOST_ERR_INVALID, "source field missing or on another device");
+    if (n_sources > 0 && (n_trace > 0 || out_walk_vals)) return fail(WOST_ERR_UNSUPPORTED, "trace / per-walk output is not available for multi-source solves");
 
     Staged<float> s_pts, s_trace, s_icdf; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
     int rc;
     if ((rc = s_pts.init(pts_xy, 2 * n_pts, false, st))) return rc;
     if ((rc = s_icdf.init(delta ? P->screened_icdf : nullptr, delta ? P->icdf_len : 0, false, st))) return rc;
-    if ((rc = s_mean.init(out_mean, n_pts, true, st)) || (rc = s_m2.init(out_m2, n_pts, true, st)) ||
-        (rc = s_blk.init(out_block_stats, 2 * n_pts * nblk, true, st)) || (rc = s_steps.init(out_steps, 1, true, st)) ||
+    if ((rc = s_mean.init(out_mean, (size_t)S * n_pts, true, st)) || (rc = s_m2.init(out_m2, (size_t)S * n_pts, true, st)) ||
+        (rc = s_blk.init(out_block_stats, (size_t)S * 2 * n_pts * nblk, true, st)) || (rc = s_steps.init(out_steps, 1, true, st)) ||
         (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * (trace_cap + 1) * 8 : 0, true, st)) ||
         (rc = s_tlen.init(out_trace_len, trace ? n_trace : 0, true, st))) return rc;
 
@@ -1058,15 +1097,23 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     long long max_vals = 1ll << 29;
     if (const char* e = std::getenv("WOST_MAX_WALK_VALS")) max_vals = std::max(1ll, std::atoll(e));
     if (W > max_vals) max_vals = W;                                     // at least one point per pass
-    const long long pts_per_pass = std::max(1ll, std::min((long long)n_pts, max_vals / W));
+    const long long pts_per_pass = std::max(1ll, std::min((long long)n_pts, max_vals / (W * S)));
     float* vals = nullptr; bool vals_temp = false;
     const bool vals_dev_out = out_walk_vals && is_device_ptr(out_walk_vals);
-    if (!vals_dev_out) { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)pts_per_pass * W, st)); vals_temp = true; }
+    if (!vals_dev_out) { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)pts_per_pass * W * S, st)); vals_temp = true; }
+    DevField* d_srcs = nullptr;
+    if (n_sources > 0) {
+        std::vector<DevField> h(n_sources);
+        for (int k = 0; k < n_sources; ++k) h[k] = sources[k]->d;
+        CU(cudaMallocAsync((void**)&d_srcs, sizeof(DevField) * n_sources, st));
+        CU(cudaMemcpyAsync(d_srcs, h.data(), sizeof(DevField) * n_sources, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));                                   // h goes out of scope
+    }
     unsigned long long* ctrs = nullptr;
     CU(cudaMallocAsync((void**)&ctrs, 2 * sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(ctrs, 0, 2 * sizeof(unsigned long long), st));
     double* blk = s_blk.dev; bool blk_temp = false;
-    if (!blk) { CU(cudaMallocAsync((void**)&blk, sizeof(double) * 2 * n_pts * nblk, st)); blk_temp = true; }
+    if (!blk) { CU(cudaMallocAsync((void**)&blk, sizeof(double) * 2 * n_pts * nblk * S, st)); blk_temp = true; }
     if (trace) {
         CU(cudaMemsetAsync(s_trace.dev, 0xff, sizeof(float) * (size_t)n_trace * (trace_cap + 1) * 8, st));   // NaN fill
         CU(cudaMemsetAsync(s_tlen.dev, 0, sizeof(int32_t) * n_trace, st));
@@ -1075,6 +1122,7 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     WalkArgs a{};
     a.dseg = scene->dseg; a.n_dseg = scene->n_dseg; a.nseg = scene->nseg; a.n_nseg = scene->n_nseg;
     a.F = dev_fields_of(fields);
+    a.n_src = n_sources; a.srcs = d_srcs;
     a.pts = s_pts.dev; a.n_pts = n_pts; a.n_walks = W;
     a.max_steps = P->max_steps; a.eps = P->eps; a.rmin = (float)((double)P->eps / 2.0);   // :167
     a.sp_mode = P->sp_mode; a.sigma_bar = P->sigma_bar;
@@ -1129,15 +1177,19 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
             a.trace = s_trace.dev + (size_t)first * (trace_cap + 1) * 8; a.trace_len = s_tlen.dev + first;
         }
         if (p0 > 0) CU(cudaMemsetAsync(ctrs, 0, sizeof(unsigned long long), st));   // walk counter only; steps accumulate
+        if (n_sources > 0) CU(cudaMemsetAsync(vals, 0, sizeof(float) * (size_t)np * W * S, st));   // rows accumulate
         kern<<<(unsigned)grid, threads, smem, st>>>(a);
         CU(cudaGetLastError());
-        block_stats_kernel<<<blocks_for(np * nblk * 32, 256), 256, 0, st>>>(a.walk_vals, np, W, nblk, blk + 2 * p0 * nblk);
+        if (n_sources > 0)
+            block_stats_kernel<<<dim3(blocks_for(np * nblk * 32, 256), S), 256, 0, st>>>(a.walk_vals, np, W, nblk, blk, S, n_pts, p0);
+        else
+            block_stats_kernel<<<blocks_for(np * nblk * 32, 256), 256, 0, st>>>(a.walk_vals, np, W, nblk, blk + 2 * p0 * nblk);
         CU(cudaGetLastError());
         if (out_walk_vals && vals_temp)
             CU(cudaMemcpyAsync(out_walk_vals + (size_t)p0 * W, vals, sizeof(float) * (size_t)np * W, cudaMemcpyDeviceToHost, st));
     }
     if (s_mean.dev || s_m2.dev) {
-        merge_stats_kernel<<<blocks_for(n_pts, 128), 128, 0, st>>>(blk, n_pts, W, nblk, s_mean.dev, s_m2.dev);
+        merge_stats_kernel<<<blocks_for((long long)S * n_pts, 128), 128, 0, st>>>(blk, (long long)S * n_pts, W, nblk, s_mean.dev, s_m2.dev);
         CU(cudaGetLastError());
     }
     if (s_steps.dev) CU(cudaMemcpyAsync(s_steps.dev, ctrs + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
@@ -1146,10 +1198,30 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
     if ((rc = s_pts.finish()) || (rc = s_icdf.finish()) || (rc = s_mean.finish()) || (rc = s_m2.finish()) || (rc = s_blk.finish()) ||
         (rc = s_steps.finish()) || (rc = s_trace.finish()) || (rc = s_tlen.finish())) return rc;
     if (vals_temp) CU(cudaFreeAsync(vals, st));
+    if (d_srcs) CU(cudaFreeAsync(d_srcs, st));
     if (blk_temp) CU(cudaFreeAsync(blk, st));
     CU(cudaFreeAsync(ctrs, st));
     if (sync) CU(cudaStreamSynchronize(st));
     return WOST_OK;
+}
+
+extern "C" {
+
+int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wost_solve_params_t* P,
+               const float* pts_xy, int64_t n_pts,
+               double* out_mean, double* out_m2, double* out_block_stats, float* out_walk_vals, uint64_t* out_steps,
+               int64_t n_trace, int32_t trace_cap, float* out_trace, int32_t* out_trace_len, void* stream) {
+    return solve_impl(scene, fields, nullptr, 0, P, pts_xy, n_pts, out_mean, out_m2, out_block_stats, out_walk_vals, out_steps,
+                      n_trace, trace_cap, out_trace, out_trace_len, stream);
+}
+
+int wost_solve_multi_source(const wost_scene_t* scene, const wost_fields_t* fields, const wost_field_t* const* sources,
+                            int32_t n_sources, const wost_solve_params_t* P, const float* pts_xy, int64_t n_pts,
+                            double* out_mean, double* out_m2, double* out_block_stats, uint64_t* out_steps, void* stream) {
+    if (n_sources < 1 || !sources) return fail(WOST_ERR_INVALID, "at least one source field is required");
+    if (n_sources > 4096) return fail(WOST_ERR_INVALID, "at most 4096 sources per call");
+    return solve_impl(scene, fields, sources, n_sources, P, pts_xy, n_pts, out_mean, out_m2, out_block_stats, nullptr, out_steps,
+                      0, 0, nullptr, nullptr, stream);
 }
 
 int wost_merge_block_stats(const double* block_stats, int64_t n_pts, int64_t n_walks, int32_t device,

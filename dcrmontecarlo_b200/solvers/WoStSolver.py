@@ -274,6 +274,25 @@ class WostSolver_2D:
         res["seed"] = seed
         return res
 
+    def solve_multi_source(self, solvePoints, sources, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None,
+                           want_block_stats=False, device_outputs=False, device=None):
+        """Shared-walk solve for many source terms (not in the reference, which re-walks per source): the walk does not
+        depend on ``f``, so one set of walks gives the estimate for every source in ``sources`` (callables or fields).
+        Returns ``mean`` / ``m2`` of shape ``(len(sources), P)``; row ``s`` equals what :meth:`solve_raw` returns with
+        ``source = sources[s]`` and the same ``seed``."""
+        nat.require_cuda()
+        device = nat.current_device() if device is None else int(device)
+        scene, fields, icdf, keep = self._device_problem(device)
+        devs = [self._dev_field(f, device) for f in sources]
+        if seed is None:
+            seed = _next_seed()
+        res = nat.solve_multi_source(scene, fields, devs, solvePoints, int(nWalks), int(maxSteps), float(eps),
+                                     delta=self.use_delta_tracking, sp_mode=self.sp_mode,
+                                     sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
+                                     want_block_stats=want_block_stats, device_outputs=device_outputs, compat=self.compat)
+        res["seed"] = seed
+        return res
+
     def solve(self, solvePoints: torch.Tensor, nWalks=1000, maxSteps=1000, eps=1e-4, return_history=False, *,
               seed=None, return_stats=False):
         """Estimate u at ``solvePoints`` ``(N, 2)`` with ``nWalks`` walks each; returns an ``(N, 1)`` float32 tensor

@@ -61,12 +61,19 @@ class DCRSurvey:
         # one solver: sigma' and sigma_bar depend on the conductivity only (no absorption in DC resistivity)
         self.solver = WostSolver_2D(dirichletBoundary, None, neumannBoundary, source=None, sigma=None, alpha=conductivity)
         self._fields = [s.field(self.sink_sign) for s in self.sources]
+        self._streams: list = []
 
-    def run(self, nWalks: int = 1000, maxSteps: int = 500, eps: float = 0.9, seed: int | None = None, streams: int = 8) -> dict:
+    def run(self, nWalks: int = 1000, maxSteps: int = 500, eps: float = 0.9, seed: int | None = None, streams: int = 8,
+            shared_walks: bool = False) -> dict:
         """Potentials at every electrode for every source.  Returns
         ``potentials`` (S, E) float64, ``stderr`` (S, E), ``dV`` (S, R) = V_M - V_N per receiver dipole, ``steps``.
         With an initialised ``torch.distributed`` group the sources are dealt round-robin to the ranks and the
-        result is gathered on every rank; the same ``seed`` gives the same numbers for any number of ranks."""
+        result is gathered on every rank; the same ``seed`` gives the same numbers for any number of ranks.
+
+        ``shared_walks=True``: the walk does not depend on the source term, so ONE set of walks per electrode serves
+        all sources (``wost_solve_multi_source``) — the cost of a survey becomes almost independent of the number of
+        source pairs.  The estimates of different sources are then correlated (same paths), which is what one wants
+        for differences between configurations; each is still an unbiased estimate of its own potential."""
         import torch.distributed as dist
 
         world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
@@ -84,8 +91,22 @@ class DCRSurvey:
         # persistent grid is sized to the work), so sources are issued round-robin on several streams with
         # device-resident results and collected once at the end.
         mine = list(range(rank, S, world))
+        if shared_walks and mine:
+            r = self.solver.solve_multi_source(self.electrodes, [self._fields[s] for s in mine], nWalks, maxSteps, eps, seed=seed)
+            for k, s in enumerate(mine):
+                pot[s], m2[s] = r["mean"][k], r["m2"][k]
+            steps += int(r["steps"][0])
+            mine = []
         n_streams = max(1, min(int(streams), len(mine)))
-        pool = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else [torch.cuda.current_stream()]
+        if n_streams > 1:
+            # streams are kept: torch's caching allocator pools memory per stream, fresh streams would re-allocate
+            while len(self._streams) < n_streams:
+                self._streams.append(torch.cuda.Stream())
+            pool = self._streams[:n_streams]
+            for st in pool:
+                st.wait_stream(torch.cuda.current_stream())
+        else:
+            pool = [torch.cuda.current_stream()]
         el_dev = self.electrodes.cuda()
         pending = []
         for i, s in enumerate(mine):

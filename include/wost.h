@@ -161,6 +161,16 @@ int wost_solve(const wost_scene_t* scene, const wost_fields_t* fields, const wos
                int64_t n_trace, int32_t trace_cap, float* out_trace, int32_t* out_trace_len,
                void* stream);
 
+/* Shared-walk solve for MANY source terms (DC-resistivity surveys: one source per current-electrode pair).  The walk of
+ * solvers/WoStSolver.py:206-291 does not depend on the source f — f only enters the contributions (:253-258) — so one
+ * set of walks serves every source: per step each source adds its own contribution, and every source's per-walk total
+ * is exactly what wost_solve with that source (fields->f is ignored here) and the same seed would produce.
+ * Outputs are source-major: out_mean[n_sources * n_pts], out_m2 likewise, out_block_stats[n_sources * n_pts * nblk * 2].
+ * The reference has no counterpart: it re-walks everything per source (tests/testGeophysicalScenario.py:137-151). */
+int wost_solve_multi_source(const wost_scene_t* scene, const wost_fields_t* fields, const wost_field_t* const* sources,
+                            int32_t n_sources, const wost_solve_params_t* params, const float* pts_xy, int64_t n_pts,
+                            double* out_mean, double* out_m2, double* out_block_stats, uint64_t* out_steps, void* stream);
+
 /* Fixed-order Chan merge of per-block (mean, M2) into per-point (mean, M2): the same device code
  * wost_solve runs internally, exposed so that gathered shards merge bit-identically.
  * block_stats[n_pts * nblk * 2]; block b holds min(WOST_WALK_BLOCK, n_walks - b*WOST_WALK_BLOCK) walks. */

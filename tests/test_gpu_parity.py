@@ -654,3 +654,48 @@ def test_reference_script_callables_give_the_scenario_results():
     b = ref5.solve_raw(s5.points, 8192, s5.max_steps, s5.eps, seed=4)
     assert int(a["steps"][0]) == int(b["steps"][0])                         # same geometry, same stream: same walks
     assert np.allclose(a["mean"], b["mean"], rtol=1e-4, atol=1e-9)
+
+
+def test_shared_walk_multi_source_equals_single_source_solves():
+    """The walk does not depend on f, so wost_solve_multi_source must reproduce, source by source, exactly what a
+    single-source solve with the same key gives — in reference mode with delta tracking (DCR), without, and in physical mode."""
+    from dcrmontecarlo_b200.survey import DCRSurvey, DipoleSource
+
+    s5 = sc.cfg5(9)
+    srcs = [DipoleSource((float(x), 0.0), (float(x) + 20.0, 0.0)).field() for x in (-40.0, -25.0, -10.0, 5.0, 20.0)]
+    solver = WostSolver_2D(PolyLinesSimple(s5.dirichlet), None, PolyLinesSimple(s5.neumann), source=srcs[0], alpha=s5.alpha)
+    multi = solver.solve_multi_source(s5.points, srcs, 2500, s5.max_steps, s5.eps, seed=12, want_block_stats=True)
+    assert multi["mean"].shape == (5, 9) and multi["block_stats"].shape == (5, 9, 3, 2)
+    for k, f in enumerate(srcs):
+        solver.setSourceTerm(f)
+        one = solver.solve_raw(s5.points, 2500, s5.max_steps, s5.eps, seed=12, want_block_stats=True)
+        assert np.array_equal(multi["mean"][k], one["mean"]) and np.array_equal(multi["m2"][k], one["m2"]), k
+        assert np.array_equal(multi["block_stats"][k], one["block_stats"])
+        assert int(multi["steps"][0]) == int(one["steps"][0])
+    # Poisson without delta tracking (mixed boundary), and the physical estimator
+    for compat in ("reference", "physical"):
+        s2 = sc.cfg2()
+        fs = [TermField.constant(-4.0), TermField.polynomial({(1, 0): 1.0, (0, 2): 2.0}), TermField.gaussian_sum([(3.0, (1.0, 1.0), 4.0)])]
+        sol = WostSolver_2D(PolyLinesSimple(s2.dirichlet), s2.g, PolyLinesSimple(s2.neumann), source=fs[0], compat=compat)
+        pts = s2.points[::25].contiguous()
+        m = sol.solve_multi_source(pts, fs, 1500, s2.max_steps, s2.eps, seed=3)
+        for k, f in enumerate(fs):
+            sol.setSourceTerm(f)
+            o = sol.solve_raw(pts, 1500, s2.max_steps, s2.eps, seed=3)
+            assert np.array_equal(m["mean"][k], o["mean"]) and np.array_equal(m["m2"][k], o["m2"]), (compat, k)
+    # bounded scratch: passes over the points do not change anything
+    import os
+    os.environ["WOST_MAX_WALK_VALS"] = str(2 * 2500 * 5)
+    try:
+        solver.setSourceTerm(srcs[0])
+        again = solver.solve_multi_source(s5.points, srcs, 2500, s5.max_steps, s5.eps, seed=12)
+    finally:
+        del os.environ["WOST_MAX_WALK_VALS"]
+    assert np.array_equal(again["mean"], multi["mean"]) and np.array_equal(again["m2"], multi["m2"])
+    # the survey driver's shared-walk mode
+    dip = [DipoleSource((float(x), 0.0), (float(x) + 20.0, 0.0)) for x in (-40.0, -10.0, 20.0)]
+    sv = DCRSurvey(PolyLinesSimple(s5.dirichlet), PolyLinesSimple(s5.neumann), s5.alpha, s5.points, dip)
+    shared = sv.run(nWalks=2048, maxSteps=s5.max_steps, eps=s5.eps, seed=8, shared_walks=True)
+    sv.solver.setSourceTerm(dip[1].field())
+    ref = sv.solver.solve_raw(s5.points, 2048, s5.max_steps, s5.eps, seed=8)
+    assert np.array_equal(shared["potentials"][1], ref["mean"])
