@@ -96,7 +96,10 @@ def cpu_baseline(n_threads=0, target_seconds=12.0):
     t0 = time.perf_counter()
     r = prob.solve(s.points[:n_pts], walks, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=2, n_threads=cores)
     dt = time.perf_counter() - t0
-    return {"value": r["steps"] / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    t1 = time.perf_counter()
+    r1 = prob.solve(s.points[:256], max(16, walks // 64), s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=3, n_threads=1)
+    single = r1["steps"] / (time.perf_counter() - t1)
+    return {"value": r["steps"] / dt, "unit": UNIT, "cores": cores, "kind": "port", "single_core_value": single,
             "sample": f"{n_pts} points x {walks} walks of the same scene ({r['steps']} steps in {dt:.2f} s), oracle/wost_oracle.c, OpenMP over points",
             "python_reference_probe": "the unmodified Python reference measured ~2.7e3 walk-steps/s on 1 core for this scene (BASELINE.md §2); it cannot travel to the GPU box"}
 
