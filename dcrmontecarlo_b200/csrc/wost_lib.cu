@@ -51,6 +51,7 @@ struct wost_scene {
 
 struct wost_field {
     int device = 0;
+    float4 support = make_float4(0.f, 0.f, 3.0e38f, 0.f);   // (cx, cy, R^2): the field is EXACTLY zero outside this disc
     DevField d{};
     wost_term_t* terms = nullptr;
     float* grid = nullptr;
@@ -79,6 +80,7 @@ struct WalkArgs {
     WideBvh nwide; int wide_coop_max;      // 32-wide Neumann hierarchy: cooperative queries when few lanes need one
     WideBvh dwide;                         // 32-wide Dirichlet hierarchy: the distance query, one warp per query
     int neu_closed; float phys_nudge;      // physical mode: closed Neumann loop?  pull-back of a reflected walker
+    const float4* src_support;             // per source (cx, cy, R^2): exactly zero outside
     int n_src; const DevField* srcs;       // shared-walk multi-source solve: n_src > 0 source fields (device array); per-walk
                                            // totals then form rows walk_vals[walk][n_src]
     long long n_trace; int trace_cap; float* trace; int* trace_len;
@@ -325,8 +327,11 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 if (a.n_src > 0) {
                     if (vis) {
                         float* row = a.walk_vals + (size_t)id * a.n_src;
+                        const float yx = x + rho * c2, yy = y + rho * s2;
                         for (int k = 0; k < a.n_src; ++k) {
-                            const float ck = field_eval(a.srcs[k], x + rho * c2, y + rho * s2) * (r * r / 4.0f);
+                            const float4 sup = __ldg(a.src_support + k);
+                            if ((yx - sup.x) * (yx - sup.x) + (yy - sup.y) * (yy - sup.y) > sup.z) continue;   // exactly zero there
+                            const float ck = field_eval(a.srcs[k], yx, yy) * (r * r / 4.0f);
                             if (ck != 0.0f) row[k] = row[k] + ck;
                         }
                     }
@@ -398,6 +403,8 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                         if (DELTA) { alpha_s = alpha_at(a.F, sx, sy); have_alpha_s = true; den = sqrtf(alpha_s * alpha_x); }
                         const float w4 = r * r / 4.0f;
                         for (int k = 0; k < a.n_src; ++k) {
+                            const float4 sup = __ldg(a.src_support + k);
+                            if ((sx - sup.x) * (sx - sup.x) + (sy - sup.y) * (sy - sup.y) > sup.z) continue;   // exactly zero there
                             const float fk = field_eval(a.srcs[k], sx, sy);
                             if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);
                         }
@@ -972,6 +979,26 @@ int wost_field_create(const wost_field_desc_t* d, int32_t device, wost_field_t**
     D.present = 1; D.kind = d->kind; D.n_terms = d->kind == WOST_FIELD_TERMS ? d->n_terms : 0; D.mask_kind = d->mask_kind;
     D.c0 = d->c0; D.m0 = d->mask[0]; D.m1 = d->mask[1]; D.m2 = d->mask[2]; D.m3 = d->mask[3]; D.outside = d->outside;
     D.nx = d->nx; D.ny = d->ny; D.x0 = d->x0; D.y0 = d->y0; D.dx = d->dx; D.dy = d->dy;
+    // compact support: a sum of Gaussian terms (no constant, no value outside a mask) evaluates to exactly zero where every
+    // term takes its underflow shortcut (exp argument < -110, wost_device.cuh); used to skip far sources in shared-walk solves
+    if (d->kind == WOST_FIELD_TERMS && d->c0 == 0.0f && D.n_terms > 0 && (d->mask_kind == WOST_MASK_NONE || d->outside == 0.0f)) {
+        bool compact = true; double mx = 0.0, my = 0.0;
+        for (int k = 0; k < D.n_terms; ++k) {
+            const wost_term_t& t = d->terms[k];
+            if (t.kind != WOST_TERM_PRODUCT || !(t.q > 0.0f)) { compact = false; break; }
+            mx += t.cx; my += t.cy;
+        }
+        if (compact) {
+            mx /= D.n_terms; my /= D.n_terms;
+            double R = 0.0;
+            for (int k = 0; k < D.n_terms; ++k) {
+                const wost_term_t& t = d->terms[k];
+                R = std::fmax(R, std::hypot(t.cx - mx, t.cy - my) + std::sqrt(112.0 / t.q));   // a little beyond e = -110
+            }
+            R = R * 1.001 + 1e-6;
+            f->support = make_float4((float)mx, (float)my, (float)(R * R), 0.0f);
+        }
+    }
     cudaError_t e = cudaSuccess;
     if (D.n_terms > 0) {
         e = cudaMalloc((void**)&f->terms, sizeof(wost_term_t) * D.n_terms);
@@ -1101,13 +1128,15 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     float* vals = nullptr; bool vals_temp = false;
     const bool vals_dev_out = out_walk_vals && is_device_ptr(out_walk_vals);
     if (!vals_dev_out) { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)pts_per_pass * W * S, st)); vals_temp = true; }
-    DevField* d_srcs = nullptr;
+    DevField* d_srcs = nullptr; float4* d_sup = nullptr;
     if (n_sources > 0) {
-        std::vector<DevField> h(n_sources);
-        for (int k = 0; k < n_sources; ++k) h[k] = sources[k]->d;
+        std::vector<DevField> h(n_sources); std::vector<float4> hs(n_sources);
+        for (int k = 0; k < n_sources; ++k) { h[k] = sources[k]->d; hs[k] = sources[k]->support; }
         CU(cudaMallocAsync((void**)&d_srcs, sizeof(DevField) * n_sources, st));
+        CU(cudaMallocAsync((void**)&d_sup, sizeof(float4) * n_sources, st));
         CU(cudaMemcpyAsync(d_srcs, h.data(), sizeof(DevField) * n_sources, cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));                                   // h goes out of scope
+        CU(cudaMemcpyAsync(d_sup, hs.data(), sizeof(float4) * n_sources, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));                                   // the host vectors go out of scope
     }
     unsigned long long* ctrs = nullptr;
     CU(cudaMallocAsync((void**)&ctrs, 2 * sizeof(unsigned long long), st));
@@ -1122,7 +1151,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     WalkArgs a{};
     a.dseg = scene->dseg; a.n_dseg = scene->n_dseg; a.nseg = scene->nseg; a.n_nseg = scene->n_nseg;
     a.F = dev_fields_of(fields);
-    a.n_src = n_sources; a.srcs = d_srcs;
+    a.n_src = n_sources; a.srcs = d_srcs; a.src_support = d_sup;
     a.pts = s_pts.dev; a.n_pts = n_pts; a.n_walks = W;
     a.max_steps = P->max_steps; a.eps = P->eps; a.rmin = (float)((double)P->eps / 2.0);   // :167
     a.sp_mode = P->sp_mode; a.sigma_bar = P->sigma_bar;
@@ -1199,6 +1228,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
         (rc = s_steps.finish()) || (rc = s_trace.finish()) || (rc = s_tlen.finish())) return rc;
     if (vals_temp) CU(cudaFreeAsync(vals, st));
     if (d_srcs) CU(cudaFreeAsync(d_srcs, st));
+    if (d_sup) CU(cudaFreeAsync(d_sup, st));
     if (blk_temp) CU(cudaFreeAsync(blk, st));
     CU(cudaFreeAsync(ctrs, st));
     if (sync) CU(cudaStreamSynchronize(st));

@@ -18,8 +18,10 @@ for n_el, n_src, W in ((21, 32, 4096), (175, 64, 1024)):
     sv = DCRSurvey(PolyLinesSimple(s.dirichlet), PolyLinesSimple(s.neumann), s.alpha, s.points, srcs)
     sv.run(nWalks=128, seed=1); sv.run(nWalks=128, seed=1, shared_walks=True)
     for label, kw in (("1 stream", dict(streams=1)), ("8 streams", dict(streams=8)), ("shared walks", dict(shared_walks=True))):
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        out = sv.run(nWalks=W, maxSteps=500, eps=0.9, seed=2, **kw)
-        dt = time.perf_counter() - t0
+        dt = 1e9
+        for rep in range(3):                                               # best of 3: the first run at a size grows the memory pool
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            out = sv.run(nWalks=W, maxSteps=500, eps=0.9, seed=2, **kw)
+            dt = min(dt, time.perf_counter() - t0)
         print(f"{n_el} electrodes x {n_src} sources x {W} walks, {label:12s}: {dt * 1e3:8.2f} ms   walk-steps taken {out['steps']:.3e}"
               f"   source-electrode estimates/s {n_el * n_src / dt:.3e}", flush=True)
