@@ -699,3 +699,22 @@ def test_shared_walk_multi_source_equals_single_source_solves():
     sv.solver.setSourceTerm(dip[1].field())
     ref = sv.solver.solve_raw(s5.points, 2048, s5.max_steps, s5.eps, seed=8)
     assert np.array_equal(shared["potentials"][1], ref["mean"])
+
+
+def test_resumable_estimate_equals_uninterrupted_run(tmp_path):
+    from dcrmontecarlo_b200.resumable import RunningEstimate
+
+    s = sc.cfg4()
+    solver = s.make_solver()
+    pts = s.points[:30].contiguous()
+    full = solver.solve_raw(pts, 5000, s.max_steps, s.eps, seed=21)
+    run = RunningEstimate(solver, pts, s.max_steps, s.eps, seed=21).add_walks(2048)
+    np.savez(tmp_path / "ckpt.npz", **run.state_dict())                      # checkpoint ...
+    state = dict(np.load(tmp_path / "ckpt.npz"))
+    resumed = RunningEstimate.from_state_dict(s.make_solver(), state)          # ... resume with a fresh solver
+    resumed.add_walks(1024).add_walks(5000 - 3072)
+    mean, se = resumed.estimate()
+    assert np.array_equal(mean, full["mean"]) and resumed.steps == int(full["steps"][0])
+    assert np.allclose(se, np.sqrt(full["m2"] / 4999 / 5000), rtol=1e-12)
+    with pytest.raises(ValueError):
+        resumed.add_walks(10)                                                # 5000 is not on a block boundary
