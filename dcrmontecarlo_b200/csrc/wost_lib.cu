@@ -63,7 +63,7 @@ struct wost_field {
 struct WalkArgs {
     const float4* dseg; int n_dseg;
     const float4* nseg; int n_nseg;
-    int stage_smem;                        // segments fit in shared memory
+    int stage_smem;                        // bit 0 / 1: Dirichlet / Neumann segment table is staged in shared memory
     DevFields F;
     const float* pts; long long n_pts; long long n_walks;
     int max_steps; float eps, rmin;
@@ -97,12 +97,19 @@ template <bool NEU, bool SRC, bool DELTA, bool TRACE, bool PHYS, bool BIG>
 __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
     extern __shared__ float4 smem[];
     const float4* dseg = a.dseg; const float4* nseg = a.nseg;
-    if (a.stage_smem) {
-        float4* sd = smem; float4* sn = smem + 2 * a.n_dseg;
-        for (int i = threadIdx.x; i < 2 * a.n_dseg; i += blockDim.x) sd[i] = a.dseg[i];
-        if (NEU) for (int i = threadIdx.x; i < 2 * a.n_nseg; i += blockDim.x) sn[i] = a.nseg[i];
-        __syncthreads();
-        dseg = sd; nseg = sn;
+    // segment tables without a hierarchy are staged into shared memory (all lanes read the same segment: broadcast);
+    // polylines with a hierarchy are read through L1 by the traversals.  stage_smem: bit 0 Dirichlet, bit 1 Neumann.
+    {
+        float4* sp = smem;
+        if (a.stage_smem & 1) {
+            for (int i = threadIdx.x; i < 2 * a.n_dseg; i += blockDim.x) sp[i] = a.dseg[i];
+            dseg = sp; sp += 2 * a.n_dseg;
+        }
+        if (NEU && (a.stage_smem & 2)) {
+            for (int i = threadIdx.x; i < 2 * a.n_nseg; i += blockDim.x) sp[i] = a.nseg[i];
+            nseg = sp;
+        }
+        if (a.stage_smem) __syncthreads();
     }
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1176,9 +1183,10 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;
-    const size_t seg_bytes = sizeof(float4) * 2 * ((size_t)scene->n_dseg + scene->n_nseg);
-    a.stage_smem = seg_bytes <= 96 * 1024 ? 1 : 0;
-    const size_t smem = a.stage_smem ? seg_bytes : 0;
+    const size_t d_bytes = scene->dbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_dseg;
+    const size_t n_bytes = scene->nbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_nseg;
+    a.stage_smem = (d_bytes + n_bytes <= 96 * 1024) ? ((d_bytes ? 1 : 0) | (n_bytes ? 2 : 0)) : 0;
+    const size_t smem = a.stage_smem ? d_bytes + n_bytes : 0;
     const bool phys = P->compat_mode == WOST_COMPAT_PHYSICAL;
     const bool big = scene->dbvh != nullptr || scene->nbvh != nullptr;
     walk_kernel_t kern = big ? (trace ? pick_kernel<true, true>(neu, src, delta, phys) : pick_kernel<false, true>(neu, src, delta, phys))
