@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
                 self.reasons |= {n for bit, n in names.items() if mask & bit}
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()

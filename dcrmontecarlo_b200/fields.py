@@ -208,40 +208,69 @@ class GridField(Field):
         self._t = torch.from_numpy(self.values)
 
     @staticmethod
-    def from_callable(fn: Callable, bounds, n: int = 257, margin: float = 0.02) -> "GridField":
-        """Tabulate ``fn(point)`` on an ``n x n`` lattice over ``bounds = [[xmin,xmax],[ymin,ymax]]``
-        grown by ``margin`` (relative) — walks may step a hair outside the Dirichlet boundary
-        (reference solvers/WoStSolver.py:206-215).  Tries one vectorised call first (the callable
-        sees ``point[0]``, ``point[1]`` as vectors) and falls back to the per-point loop."""
+    def _evaluate(fn: Callable, X: torch.Tensor, Y: torch.Tensor, vectorised):
+        """``fn`` on every (X, Y) pair -> (flat float32 values, vectorised?).  One vectorised call is tried first (the
+        callable sees ``point[0]``, ``point[1]`` as vectors) and verified on a few points; else the per-point loop.
+        No torch.no_grad(): callables may differentiate internally (the solver's sigma' does)."""
+        xf, yf = X.flatten(), Y.flatten()
+        N = xf.numel()
+
+        def one(i):
+            v = fn(torch.stack([xf[i], yf[i]]))
+            return float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
+
+        if vectorised is not False:
+            try:
+                out = torch.as_tensor(fn(torch.stack([xf, yf], dim=0)), dtype=torch.float32).detach()
+                if out.shape == (N,):
+                    probe = [0, N // 3, N // 2 + 7, N - 1]
+                    if vectorised is True or all(abs(one(i) - float(out[i])) <= 1e-5 * (1.0 + abs(float(out[i]))) for i in probe):
+                        return out, True
+            except Exception:
+                pass
+        flat = torch.empty(N, dtype=torch.float32)
+        for i in range(N):
+            flat[i] = one(i)
+        return flat, False
+
+    @staticmethod
+    def from_callable(fn: Callable, bounds, n: int = 257, margin: float = 0.02, tol: float | None = None,
+                      n_max: int = 2049) -> "GridField":
+        """Tabulate ``fn(point)`` on an ``n x n`` lattice over ``bounds = [[xmin,xmax],[ymin,ymax]]`` grown by ``margin``
+        (relative) — walks may step a hair outside the Dirichlet boundary (reference solvers/WoStSolver.py:206-215).
+
+        Error control: with ``tol`` the bilinear interpolant is compared with ``fn`` at the cell centres (where its error
+        peaks) and the lattice is refined (n -> 2n-1, nodes are reused) until the largest error is below ``tol`` times
+        the value range, or ``n_max`` is reached (then a warning is issued).  The achieved error is kept in
+        ``.interp_error``.  Only attempted for callables that can be evaluated in one vectorised call."""
         (xmin, xmax), (ymin, ymax) = [[float(b[0]), float(b[1])] for b in bounds]
         mx, my = margin * (xmax - xmin), margin * (ymax - ymin)
-        xs = torch.linspace(xmin - mx, xmax + mx, n)
-        ys = torch.linspace(ymin - my, ymax + my, n)
-        X, Y = torch.meshgrid(xs, ys, indexing="ij")
-        vals = None
-        # no torch.no_grad() here: callables may differentiate internally (the solver's sigma' does)
-        try:
-            out = fn(torch.stack([X.flatten(), Y.flatten()], dim=0))
-            out = torch.as_tensor(out, dtype=torch.float32).detach()
-            if out.shape == (n * n,):
-                probe = [0, n * n // 3, n * n // 2 + 7, n * n - 1]
-                def one(i):
-                    v = fn(torch.stack([X.flatten()[i], Y.flatten()[i]]))
-                    return float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
+        vectorised = None
+        while True:
+            xs = torch.linspace(xmin - mx, xmax + mx, n)
+            ys = torch.linspace(ymin - my, ymax + my, n)
+            X, Y = torch.meshgrid(xs, ys, indexing="ij")
+            flat, vectorised = GridField._evaluate(fn, X, Y, vectorised)
+            gf = GridField(flat.reshape(n, n).numpy(), float(xs[0]), float(ys[0]), float(xs[1] - xs[0]), float(ys[1] - ys[0]))
+            gf.interp_error = None
+            if tol is None or not vectorised:
+                return gf
+            xc, yc = 0.5 * (xs[:-1] + xs[1:]), 0.5 * (ys[:-1] + ys[1:])
+            Xc, Yc = torch.meshgrid(xc, yc, indexing="ij")
+            exact, _ = GridField._evaluate(fn, Xc, Yc, True)
+            approx = gf(torch.stack([Xc.flatten(), Yc.flatten()], dim=1))
+            finite = torch.isfinite(exact)
+            scale = float((flat[torch.isfinite(flat)].max() - flat[torch.isfinite(flat)].min()).abs()) + 1e-30
+            gf.interp_error = float((approx - exact)[finite].abs().max()) / scale if finite.any() else 0.0
+            if gf.interp_error <= tol:
+                return gf
+            if 2 * n - 1 > n_max:
+                import warnings
 
-                ok = all(abs(one(i) - float(out[i])) <= 1e-5 * (1.0 + abs(float(out[i]))) for i in probe)
-                if ok:
-                    vals = out.reshape(n, n)
-        except Exception:
-            vals = None
-        if vals is None:
-            flat = torch.empty(n * n, dtype=torch.float32)
-            xf, yf = X.flatten(), Y.flatten()
-            for i in range(n * n):
-                v = fn(torch.stack([xf[i], yf[i]]))
-                flat[i] = float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
-            vals = flat.reshape(n, n)
-        return GridField(vals.numpy(), float(xs[0]), float(ys[0]), float(xs[1] - xs[0]), float(ys[1] - ys[0]))
+                warnings.warn(f"tabulated field: interpolation error {gf.interp_error:.2e} of the value range at n={n} "
+                              f"(tolerance {tol:.1e}); pass an analytic fields.TermField for an exact device field")
+                return gf
+            n = 2 * n - 1
 
     def _raw(self, x, y):
         fx = torch.clamp((x - self.x0) / self.dx, 0.0, float(self.nx - 1))
@@ -261,7 +290,7 @@ class GridField(Field):
                     x0=self.x0, y0=self.y0, dx=self.dx, dy=self.dy)
 
 
-def as_field(obj, bounds=None, n: int = 257, trace: bool = True) -> Field | None:
+def as_field(obj, bounds=None, n: int = 257, trace: bool = True, tol: float | None = None) -> Field | None:
     """``None`` stays ``None``; numbers become constants; Field passes through; any other callable is first traced
     symbolically into an exact :class:`TermField` (:mod:`fieldtrace`) and, if that is not possible, tabulated."""
     if obj is None or isinstance(obj, Field):
@@ -280,7 +309,7 @@ def as_field(obj, bounds=None, n: int = 257, trace: bool = True) -> Field | None
             exact = trace_callable(obj, bounds)
             if exact is not None:
                 return exact
-        return GridField.from_callable(obj, bounds, n=n)
+        return GridField.from_callable(obj, bounds, n=n, tol=tol)
     raise TypeError(f"cannot turn {type(obj)} into a field")
 
 

@@ -51,7 +51,7 @@ class WostSolver_2D:
     def __init__(self, dirichletBoundary: PolyLines, dirichletBoundaryFunction: callable = None,
                  neumannBoundary: PolyLines = None, source: callable = None, sigma: callable = None,
                  alpha: callable = None, *, field_resolution: int = 257, sigma_prime_resolution: int = 65,
-                 sigma_prime_mode: str = "auto", compat: str = "reference"):
+                 sigma_prime_mode: str = "auto", compat: str = "reference", field_tolerance: float | None = 1e-3):
         """``sigma_prime_mode``: ``"auto"`` differentiates the coefficients like the reference and falls back to
         ``sigma/alpha`` when that fails; ``"ratio"`` forces the fallback — what the reference ends up with for
         callables that wrap their result in ``torch.tensor(...)`` (tests/testWostVariableCoefficients.py:49,57,
@@ -66,6 +66,7 @@ class WostSolver_2D:
         if compat not in nat.COMPAT:
             raise ValueError("compat must be 'reference' or 'physical'")
         self.compat = compat
+        self.field_tolerance = field_tolerance       # callables that must be tabulated: refine the table to this relative error
         if sigma_prime_mode not in ("auto", "ratio", "full"):
             raise ValueError("sigma_prime_mode must be 'auto', 'ratio' or 'full'")
         self.sigma_prime_mode = sigma_prime_mode
@@ -209,7 +210,9 @@ class WostSolver_2D:
     def _host_field(self, obj, n=None):
         key = ("host", id(obj), n)
         if key not in self._cache:
-            self._cache[key] = (obj, as_field(obj, bounds=self._bounds(), n=n or self.field_resolution))
+            # sigma' tables (explicit n) evaluate autograd point by point: fixed resolution; everything else is refined
+            self._cache[key] = (obj, as_field(obj, bounds=self._bounds(), n=n or self.field_resolution,
+                                              tol=None if n else self.field_tolerance))
         return self._cache[key][1]
 
     def _dev_field(self, obj, device, n=None):

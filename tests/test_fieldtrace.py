@@ -178,3 +178,22 @@ def test_wrong_trace_is_rejected_by_the_numerical_check():
         return p[0] * (1.0 if state["n"] == 1 else 2.0)
 
     assert trace_callable(impure, B) is None
+
+
+def test_tabulation_error_control():
+    import warnings
+
+    smooth = lambda p: 1.0 / (1.0 + p[0] ** 2 + p[1] ** 2)                      # noqa: E731  (rational: not traceable)
+    coarse = GridField.from_callable(smooth, B, n=9)
+    fine = GridField.from_callable(smooth, B, n=9, tol=1e-4)
+    assert coarse.interp_error is None and coarse.nx == 9
+    assert fine.nx > 9 and fine.interp_error <= 1e-4
+    exact = torch.stack([smooth(p) for p in Q[:200]])
+    assert (fine(Q[:200]) - exact).abs().max() < 2e-4 < (coarse(Q[:200]) - exact).abs().max()
+    steep = lambda p: torch.tanh(400.0 * p[0])                                  # noqa: E731  (cannot be resolved by n_max)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        g = GridField.from_callable(steep, B, n=17, tol=1e-3, n_max=129)
+    assert g.nx == 129 and g.interp_error > 1e-3 and any("interpolation error" in str(x.message) for x in w)
+    branchy = lambda p: 1.0 if float(p[0]) > 0 else -1.0                        # noqa: E731  (loop path: no refinement)
+    assert GridField.from_callable(branchy, B, n=9, tol=1e-6).nx == 9
