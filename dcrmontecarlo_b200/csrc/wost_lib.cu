@@ -428,18 +428,21 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 }
             }
             if (DELTA) {                                                                // :271-284
-                // alpha(current_point) is the value computed when the walker arrived here (same function, same point)
-                if (u24(o[1]) > sbgn) {
-                    const float alpha_q = alpha_at(a.F, qx, qy);
-                    atten = atten * sqrtf(alpha_q / alpha_x);
-                    x = qx; y = qy; alpha_x = alpha_q;
+                // alpha(current_point) is the value computed when the walker arrived here (same function, same point).
+                // Both branches need alpha at their destination: evaluate it at ONE call site for all lanes (the edge
+                // branch at next_point, the interior branch at sample_point unless the source term already did).
+                const bool edge = u24(o[1]) > sbgn;
+                const float tx = edge ? qx : sx, ty = edge ? qy : sy;
+                const float alpha_t = (!edge && have_alpha_s) ? alpha_s : alpha_at(a.F, tx, ty);
+                const float ratio = sqrtf(alpha_t / alpha_x);
+                if (edge) {
+                    atten = atten * ratio;                                              // :277
                 } else {
-                    if (!have_alpha_s) alpha_s = alpha_at(a.F, sx, sy);
-                    const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy);
-                    const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);
-                    atten = (atten * sqrtf(alpha_s / alpha_x)) * sc;
-                    x = sx; y = sy; alpha_x = alpha_s;
+                    const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy);            // :281
+                    const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);              // :282
+                    atten = (atten * ratio) * sc;                                       // :283
                 }
+                x = tx; y = ty; alpha_x = alpha_t;                                      // :278,284
             } else { x = qx; y = qy; }                                                  // :287
             ++steps;                                                                    // :291
         }
