@@ -207,7 +207,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
     prm.n_walks, prm.max_steps, prm.eps = int(n_walks), int(max_steps), float(eps)
     prm.delta_tracking, prm.sp_mode, prm.sigma_bar = int(bool(delta)), int(sp_mode), float(sigma_bar)
     icdf_keep = None
-    if delta:
+    if delta and icdf is not None:
         icdf_keep = icdf if (isinstance(icdf, torch.Tensor) and icdf.is_cuda) else host_f32(icdf)
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
@@ -258,7 +258,7 @@ def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int,
     prm.n_walks, prm.max_steps, prm.eps = int(n_walks), int(max_steps), float(eps)
     prm.delta_tracking, prm.sp_mode, prm.sigma_bar = int(bool(delta)), int(sp_mode), float(sigma_bar)
     icdf_keep = None
-    if delta:
+    if delta and icdf is not None:
         icdf_keep = icdf if (isinstance(icdf, torch.Tensor) and icdf.is_cuda) else host_f32(icdf)
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)

@@ -80,6 +80,7 @@ struct WalkArgs {
     WideBvh nwide; int wide_coop_max;      // 32-wide Neumann hierarchy: cooperative queries when few lanes need one
     WideBvh dwide;                         // 32-wide Dirichlet hierarchy: the distance query, one warp per query
     int neu_closed; float phys_nudge;      // physical mode: closed Neumann loop?  pull-back of a reflected walker
+    float phys_rcap;                       // physical mode with variable coefficients: step radius cap 1/sqrt(sigma_bar)
     const float4* src_support;             // per source (cx, cy, R^2): exactly zero outside
     int n_src; const DevField* srcs;       // shared-walk multi-source solve: n_src > 0 source fields (device array); per-walk
                                            // totals then form rows walk_vals[walk][n_src]
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 dD = 1.0f;                                             // :190 sentinel (Q6)
                 atten = 1.0f; total_v = 0.0f; onB = false; phi_n = 0.0f; steps = 0;   // :188-195
                 if (DELTA) alpha_x = alpha_at(a.F, x, y);
+                if (PHYS && DELTA) atten = 1.0f / sqrtf(alpha_x);          // u = U / sqrt(alpha): the walk estimates U
                 active = true;
             }
             const unsigned long long cnt = (unsigned long long)__popc(need);
@@ -168,14 +170,15 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         int dir_arg = -1;
         if (PHYS && active)
             dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, &dir_arg) : dirichlet_distance(dseg, a.n_dseg, x, y, &dir_arg);
-        const bool stepping = active && steps < a.max_steps && dD > a.eps;
+        const bool stepping = active && steps < a.max_steps && dD > a.eps && !(PHYS && DELTA && atten == 0.0f);   // weight 0: absorbed
         if (active && !stepping) {
             // terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7)
             float gx_ = x, gy_ = y;
             if (PHYS && dir_arg >= 0) segment_closest_point(a.dseg[2 * dir_arg], a.dseg[2 * dir_arg + 1], x, y, gx_, gy_);
             float bc = 0.0f;
             if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, gx_, gy_) : field_eval_inl(a.F.g, gx_, gy_);
-            if (DELTA) bc = bc * atten;
+            if (PHYS && DELTA) bc = atten * (bc * sqrtf(alpha_at(a.F, gx_, gy_)));   // U = sqrt(alpha) g on the boundary
+            else if (DELTA) bc = bc * atten;
             if (SRC && a.n_src > 0) {                                     // one total per source: same walk, same boundary term
                 float* row = a.walk_vals + (size_t)id * a.n_src;
                 for (int k = 0; k < a.n_src; ++k) row[k] = row[k] + bc;
@@ -310,19 +313,24 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             }
         }
         if (stepping) {
-            if (NEU) { const float m = dN < dD ? dN : dD; r = (m > a.rmin) ? m : a.rmin; }   // :212
-            else r = (dD > a.rmin) ? dD : a.rmin;                                       // :215
+            float m = NEU ? (dN < dD ? dN : dD) : dD;                                   // :212 / :215
+            if (PHYS && DELTA) m = m < a.phys_rcap ? m : a.phys_rcap;                   // keeps r sqrt(sigma_bar) <= 1
+            r = (m > a.rmin) ? m : a.rmin;
         }
 
         // ---- phase C: move, source sample, delta tracking ---------------------------------------------------------
         if (stepping) {
             float qx, qy;
-            if (PHYS && SRC) {
+            // physical + variable coefficients: volume sample y, its visibility and kernel ratio, Bessel terms of this ball
+            float pd_yx = 0.f, pd_yy = 0.f, pd_ratio = 1.0f, pd_i0c = 1.0f, pd_k0c = 0.0f, pd_qc = 0.0f, pd_m1 = 0.0f;
+            bool pd_vis = true;
+            if (PHYS && (SRC || DELTA)) {
                 // source sample (physical): independent direction, rho^2/r^2 ~ -ln  <=>  rho ~ 4 rho ln(r/rho)/r^2 (the 2D
                 // disc Green's function), counted only if visible from x inside the star-shaped region
                 const float th2 = (NEU && onB) ? phi_n + (u24(o[1]) - 0.5f) * 3.14159274101257324f : (u24(o[1]) * 2.0f) * 3.14159274101257324f;
                 float s2, c2; sincosf(th2, &s2, &c2);
-                const float rho = r * sqrtf(u24p(o[2]) * u24p(o[3]));
+                const float u23 = u24p(o[2]) * u24p(o[3]);
+                const float rho = r * sqrtf(u23);
                 bool vis = true;
                 if (NEU && gap <= rho && ray_may_hit_disc(x, y, c2, s2, a.ndisc_x, a.ndisc_y, a.ndisc_r2)) {
                     float vs; int vk;
@@ -330,32 +338,56 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                     else ray_cast<true>(nseg, a.n_nseg, x, y, c2, s2, vs, vk);
                     vis = vk < 0 || vs > rho;
                 }
+                const float yx = x + rho * c2, yy = y + rho * s2;
+                float wsrc = r * r / 4.0f;                                              // |G| of the Laplace ball kernel
+                if (DELTA) {
+                    // screened ball kernel G = ratio(rho) G_laplace; the source of the transformed equation is f / sqrt(alpha)
+                    const float c = r * a.sqrt_sigma_bar;
+                    float sc;
+                    pd_qc = 0.25f * (c * c);
+                    bessel_i0m1_s(pd_qc, pd_m1, sc);
+                    pd_i0c = 1.0f + pd_m1;
+                    pd_k0c = sc - (0.5f * logf(pd_qc) + EULER_GAMMA) * pd_i0c;
+                    pd_ratio = phys_green_ratio(pd_i0c, sc, pd_qc * u23, -0.5f * logf(u23));
+                    pd_yx = yx; pd_yy = yy; pd_vis = vis;
+                    if (SRC && vis) wsrc = atten * ((pd_ratio * wsrc) / sqrtf(alpha_at(a.F, yx, yy)));
+                }
                 float pc = 0.0f;
-                if (a.n_src > 0) {
+                if (SRC && a.n_src > 0) {
                     if (vis) {
                         float* row = a.walk_vals + (size_t)id * a.n_src;
-                        const float yx = x + rho * c2, yy = y + rho * s2;
                         for (int k = 0; k < a.n_src; ++k) {
                             const float4 sup = __ldg(a.src_support + k);
                             if ((yx - sup.x) * (yx - sup.x) + (yy - sup.y) * (yy - sup.y) > sup.z) continue;   // exactly zero there
-                            const float ck = field_eval(a.srcs[k], yx, yy) * (r * r / 4.0f);
+                            const float ck = field_eval(a.srcs[k], yx, yy) * wsrc;
                             if (ck != 0.0f) row[k] = row[k] + ck;
                         }
                     }
-                } else {
-                    pc = vis ? field_eval_inl(a.F.f, x + rho * c2, y + rho * s2) * (r * r / 4.0f) : 0.0f;
+                } else if (SRC) {
+                    pc = vis ? (DELTA ? field_eval(a.F.f, yx, yy) : field_eval_inl(a.F.f, yx, yy)) * wsrc : 0.0f;
                     total_v += pc;
                 }
-                if (TRACE) {
+                if (TRACE && SRC) {
                     if ((long long)id < a.n_trace && steps < a.trace_cap)
-                        reinterpret_cast<float4*>(a.trace)[((size_t)id * (a.trace_cap + 1) + steps) * 2 + 1] = make_float4(x + rho * c2, y + rho * s2, pc, 0.0f);
+                        reinterpret_cast<float4*>(a.trace)[((size_t)id * (a.trace_cap + 1) + steps) * 2 + 1] = make_float4(yx, yy, pc, 0.0f);
                 }
+            }
+            // physical + variable coefficients: null-collision inside the star with probability 1 - 1/I0(c), else walk on
+            bool pd_vol = false;
+            if (PHYS && DELTA) {
+                uint32_t o2[4];
+                philox4x32_10(pidx, widx, (uint32_t)steps, 3u, a.key0, a.key1, o2);     // stream tag 3: branch choice
+                pd_vol = u24(o2[0]) < pd_m1 / pd_i0c;
             }
             if (NEU) {
                 if (PHYS) {
                     // a wall within r + nudge counts as hit, so a free step ends at least `nudge` short of every wall
                     if (best_k < 0 || best_s > r + a.phys_nudge) { qx = x + r * ex; qy = y + r * ey; onB = false; }
                     else {
+                        if (DELTA && !pd_vol) {                                         // flux of the screened kernel through the wall
+                            const float ct = fminf(best_s, r) * a.sqrt_sigma_bar;
+                            atten = atten * phys_wall_weight(pd_i0c, pd_k0c, 0.25f * (ct * ct));
+                        }
                         // reflect: sit `nudge` off the wall on the side we came from, remember that side's normal
                         const float4 s1 = nseg[2 * best_k + 1];
                         float nx = s1.x, ny = s1.y;
@@ -379,9 +411,19 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 }
             }
 
+            if (PHYS && DELTA && pd_vol) {
+                if (!pd_vis) { atten = 0.0f; qx = x; qy = y; }                          // the sample fell behind a wall
+                else {
+                    const float sp = sigma_prime_at(a.F, a.sp_mode, pd_yx, pd_yy);
+                    atten = (atten * (pd_ratio * (pd_qc * pd_i0c / pd_m1))) * (1.0f - sp / a.sigma_bar);
+                    qx = pd_yx; qy = pd_yy;
+                }
+                onB = false;
+            }
+
             float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f, alpha_s = 1.0f;
             bool have_alpha_s = false;
-            if (DELTA) {
+            if (DELTA && !PHYS) {
                 sbgn = interior_probability(r * a.sqrt_sigma_bar);                      // sigma_bar * |G^sb|(r)
                 gn = sbgn * a.inv_sigma_bar;                                            // screenedGreensNorm2D (utils.py:29-44)
             }
@@ -427,7 +469,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                         reinterpret_cast<float4*>(a.trace)[((size_t)id * (a.trace_cap + 1) + steps) * 2 + 1] = make_float4(sx, sy, contrib, 0.0f);
                 }
             }
-            if (DELTA) {                                                                // :271-284
+            if (DELTA && !PHYS) {                                                       // :271-284
                 // alpha(current_point) is the value computed when the walker arrived here (same function, same point).
                 // Both branches need alpha at their destination: evaluate it at ONE call site for all lanes (the edge
                 // branch at next_point, the interior branch at sample_point unless the source term already did).
@@ -811,12 +853,16 @@ typedef void (*walk_kernel_t)(const WalkArgs);
 template <bool TRACE, bool BIG>
 static walk_kernel_t pick_kernel(bool neu, bool src, bool delta, bool phys) {
     const int m = (neu ? 4 : 0) | (src ? 2 : 0) | (delta ? 1 : 0);
-    if (phys) {                                        // physical mode: constant coefficients only (checked by the caller)
+    if (phys) {                                        // physical mode; delta = variable coefficients
         switch (m) {
             case 0: return walk_kernel<false, false, false, TRACE, true, BIG>;
+            case 1: return walk_kernel<false, false, true, TRACE, true, BIG>;
             case 2: return walk_kernel<false, true, false, TRACE, true, BIG>;
+            case 3: return walk_kernel<false, true, true, TRACE, true, BIG>;
             case 4: return walk_kernel<true, false, false, TRACE, true, BIG>;
-            default: return walk_kernel<true, true, false, TRACE, true, BIG>;
+            case 5: return walk_kernel<true, false, true, TRACE, true, BIG>;
+            case 6: return walk_kernel<true, true, false, TRACE, true, BIG>;
+            default: return walk_kernel<true, true, true, TRACE, true, BIG>;
         }
     }
     switch (m) {
@@ -1092,11 +1138,13 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
         return fail(WOST_ERR_INVALID, "point and walk indices must fit 32 bits (Philox counter words)");
     const bool delta = P->delta_tracking != 0;
     if (P->compat_mode != WOST_COMPAT_REFERENCE && P->compat_mode != WOST_COMPAT_PHYSICAL) return fail(WOST_ERR_INVALID, "unknown compat_mode");
-    if (P->compat_mode == WOST_COMPAT_PHYSICAL && delta)
-        return fail(WOST_ERR_UNSUPPORTED, "physical mode covers constant coefficients only (no delta tracking)");
+    const bool phys_delta = P->compat_mode == WOST_COMPAT_PHYSICAL && delta;
     if (delta) {
         if (!(P->sigma_bar > 0.0f)) return fail(WOST_ERR_INVALID, "delta tracking needs sigma_bar > 0");
-        if (!P->screened_icdf || P->icdf_len < 2) return fail(WOST_ERR_INVALID, "delta tracking needs the screened radius table");
+        if (!phys_delta && (!P->screened_icdf || P->icdf_len < 2)) return fail(WOST_ERR_INVALID, "delta tracking needs the screened radius table");
+        // physical mode: the weights are power series in (r sqrt(sigma_bar))^2 / 4, r <= max(1/sqrt(sigma_bar), eps/2)
+        if (phys_delta && !((double)P->eps / 2.0 * sqrt((double)P->sigma_bar) <= 2.0))
+            return fail(WOST_ERR_INVALID, "physical mode: eps/2 * sqrt(sigma_bar) must be <= 2 (the smallest step must resolve the absorption length)");
         if (P->sp_mode < WOST_SP_FULL || P->sp_mode > WOST_SP_FIELD) return fail(WOST_ERR_INVALID, "unknown sp_mode");
         if (P->sp_mode == WOST_SP_FIELD && !(fields && fields->sigma_prime)) return fail(WOST_ERR_INVALID, "WOST_SP_FIELD needs fields.sigma_prime");
     }
@@ -1122,7 +1170,8 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     Staged<float> s_pts, s_trace, s_icdf; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
     int rc;
     if ((rc = s_pts.init(pts_xy, 2 * n_pts, false, st))) return rc;
-    if ((rc = s_icdf.init(delta ? P->screened_icdf : nullptr, delta ? P->icdf_len : 0, false, st))) return rc;
+    const bool use_icdf = delta && !phys_delta;
+    if ((rc = s_icdf.init(use_icdf ? P->screened_icdf : nullptr, use_icdf ? P->icdf_len : 0, false, st))) return rc;
     if ((rc = s_mean.init(out_mean, (size_t)S * n_pts, true, st)) || (rc = s_m2.init(out_m2, (size_t)S * n_pts, true, st)) ||
         (rc = s_blk.init(out_block_stats, (size_t)S * 2 * n_pts * nblk, true, st)) || (rc = s_steps.init(out_steps, 1, true, st)) ||
         (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * (trace_cap + 1) * 8 : 0, true, st)) ||
@@ -1183,6 +1232,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.dbvh.nodes = scene->dbvh; a.dbvh.n_leaves = scene->dbvh_leaves; a.nbvh.nodes = scene->nbvh; a.nbvh.cones = scene->ncones; a.nbvh.n_leaves = scene->nbvh_leaves;
     a.dwide = scene->dwide; a.nwide = scene->nwide; a.wide_coop_max = env_int("WOST_WIDE_COOP_MAX", 20);
     a.bvh_slack = scene->bvh_slack; a.neu_closed = scene->neu_closed; a.phys_nudge = scene->phys_nudge;
+    a.phys_rcap = phys_delta ? 1.0f / sqrtf(P->sigma_bar) : 0.0f;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;

@@ -263,5 +263,42 @@ def phys_cylinder(n_seg: int = 256) -> Scenario:
                     analytic=lambda p: p[:, 0] * (1.0 + R * R / (p[:, 0] ** 2 + p[:, 1] ** 2)))
 
 
+def phys_varcoef_dirichlet() -> Scenario:
+    """The reference's own correctness problem (tests/testWoStCorrectness.py:81-196: u = (1-x^2)(1-y^2), alpha = 2+.5x+.5y,
+    sigma = 2+xy) solved by delta tracking done by the book.  The reference's estimator plateaus at RMSE 0.028 on it
+    (cfg 1b); this one converges to the analytic solution."""
+    s = cfg1b()
+    s.name, s.compat, s.sp_mode, s.sigma_bar = "phys_varcoef_dirichlet", "physical", SP_FULL, None
+    return s
+
+
+def phys_varcoef_neumann_top() -> Scenario:
+    """Variable coefficients with a reflecting wall: unit square, zero-Neumann top edge,
+    alpha = (1 + 0.3 x)(1 + 0.5 (1-y)^2)  (d alpha/dy = 0 on the wall), sigma = 0.5 + x,
+    u = (1 + x) cos(pi (1-y)),  f = -div(alpha grad u) + sigma u  expanded into polynomial x trig terms."""
+    d, n, pts = _unit_square_neumann_top()
+    pi = float(np.float32(math.pi))
+    X, Y, ONE = {(1, 0): 1.0}, {(0, 1): 1.0}, {(0, 0): 1.0}
+    omy = _padd(ONE, _pscale(Y, -1.0))                                    # 1 - y
+    omy2 = _pmul(omy, omy)
+    ax = _padd(ONE, _pscale(X, 0.3))                                      # 1 + 0.3 x
+    ay = _padd(ONE, _pscale(omy2, 0.5))                                   # 1 + 0.5 (1-y)^2
+    alpha = _pmul(ax, ay)
+    alpha_x = _pscale(ay, 0.3)
+    alpha_y = _pscale(_pmul(ax, omy), -1.0)
+    opx = _padd(ONE, X)                                                   # 1 + x
+    sigma = {(0, 0): 0.5, (1, 0): 1.0}
+    # u_x = C, u_y = pi (1+x) S, u_yy = -pi^2 (1+x) C   with C = cos(pi (1-y)), S = sin(pi (1-y))
+    cos_poly = _padd(_pscale(alpha_x, -1.0), _pscale(_pmul(alpha, opx), math.pi ** 2), _pmul(sigma, opx))
+    sin_poly = _pscale(_pmul(alpha_y, opx), -math.pi)
+    terms = [make_term(A=c, px=i, py=j, trig1=("cos", 0.0, -pi, pi)) for (i, j), c in cos_poly.items()]
+    terms += [make_term(A=c, px=i, py=j, trig1=("sin", 0.0, -pi, pi)) for (i, j), c in sin_poly.items()]
+    g = TermField(0.0, [make_term(A=1.0, trig1=("cos", 0.0, -pi, pi)), make_term(A=1.0, px=1, trig1=("cos", 0.0, -pi, pi))])
+    return Scenario(name="phys_varcoef_neumann_top", dirichlet=d, neumann=n, points=pts, g=g, f=TermField(0.0, terms),
+                    alpha=TermField.polynomial(alpha), sigma=TermField.polynomial(sigma), n_walks=20000, max_steps=2000,
+                    eps=1e-4, compat="physical", analytic=lambda p: (1.0 + p[:, 0]) * torch.cos(math.pi * (1.0 - p[:, 1])))
+
+
+PHYSICAL_VARCOEF = {"phys_varcoef_dirichlet": phys_varcoef_dirichlet, "phys_varcoef_neumann": phys_varcoef_neumann_top}
 PHYSICAL = {"phys_laplace": phys_laplace_neumann_top, "phys_poisson": phys_poisson_neumann_top, "phys_cylinder": phys_cylinder}
 ALL = {"cfg1a": cfg1a, "cfg1b": cfg1b, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}

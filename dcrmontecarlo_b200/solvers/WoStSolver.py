@@ -58,11 +58,12 @@ class WostSolver_2D:
         SURVEY Q12) — and ``"full"`` insists on the differentiated form.
 
         ``compat``: ``"reference"`` (default) reproduces the reference's estimator, quirks included (SURVEY §0);
-        ``"physical"`` runs textbook Walk on Stars for constant coefficients — first hit by ray distance, reflection
-        into the hemisphere facing the domain, the closing vertex of a closed loop is a silhouette candidate,
-        termination projects onto the Dirichlet boundary, Green's-function source sampling with visibility.  It is not
-        part of the reference (whose mixed-boundary walks leak through Neumann walls, Q1/Q2) and is validated against
-        analytic mixed-boundary solutions instead."""
+        ``"physical"`` runs textbook Walk on Stars — first hit by ray distance, reflection into the hemisphere facing the
+        domain, the closing vertex of a closed loop is a silhouette candidate, termination projects onto the Dirichlet
+        boundary, Green's-function source sampling with visibility; variable ``alpha`` / ``sigma`` by delta tracking
+        with the screened kernel's proper weights and a true majorant (Neumann walls then need ``d alpha/dn = 0``).  It is
+        not part of the reference (whose mixed-boundary walks leak through Neumann walls, Q1/Q2, and whose delta-tracking
+        estimator is biased, Q8/Q9/Q13) and is validated against analytic solutions instead."""
         if compat not in nat.COMPAT:
             raise ValueError("compat must be 'reference' or 'physical'")
         self.compat = compat
@@ -93,6 +94,9 @@ class WostSolver_2D:
             self._sigma_given, self._alpha_given = sigma is not None, alpha is not None
             self.sigma_prime, self.sigma_bar = self.buildModifiedSigma()
             self.use_delta_tracking = True
+            if compat == "physical":
+                self.sigma_bar = self._physical_majorant()
+                self.use_delta_tracking = self.sigma_bar > 0.0           # constant alpha, no absorption: plain WoSt
 
     # ------------------------------------------------------------------------------------------------
     # setup (host): sigma' and sigma_bar, reference :66-138
@@ -163,6 +167,33 @@ class WostSolver_2D:
                 return vals.min().item(), vals.max().item()
         lo, hi, _, _ = gridSampleMinMax(sigma_prime, self.domain_bounds, grid_resolution=50)
         return lo, hi
+
+    def _physical_majorant(self, n: int = 129) -> float:
+        """``compat="physical"``: delta tracking needs a true majorant ``sigma_bar >= |sigma'|`` (the reference takes the
+        *range* of sigma' on a 50x50 lattice and 10.0 when that looks odd, ``:130-136``).  Here: 1.05 x the
+        largest ``|sigma'|`` on an n x n lattice over the bounding box, with sigma' in its differentiated form."""
+        import warnings
+
+        hosts = [(self._host_field(c) if given else None) for c, given in ((self.alpha, self._alpha_given), (self.sigma, self._sigma_given))]
+        if all(h is None or isinstance(h, TermField) for h in hosts):
+            if self.sigma_prime_mode != "ratio":
+                self.sp_mode = SP_FULL if self._alpha_given else SP_RATIO    # closed form on the device, whatever autograd said
+            keep = (self.alpha, self.sigma)
+            try:
+                self.alpha, self.sigma = (hosts[0] if self._alpha_given else self.alpha), (hosts[1] if self._sigma_given else self.sigma)
+                vals = self._sigma_prime_lattice_vectorised(n)
+            finally:
+                self.alpha, self.sigma = keep
+        else:
+            if self._autograd_failed and self._alpha_given and self.sigma_prime_mode != "ratio":
+                warnings.warn("compat='physical': alpha could not be differentiated, sigma' falls back to sigma/alpha "
+                              "(exact only where alpha is constant)", RuntimeWarning)
+            lo, hi, _, _ = gridSampleMinMax(self.sigma_prime, self.domain_bounds, grid_resolution=min(n, 65))
+            vals = torch.tensor([lo, hi])
+        vals = vals[torch.isfinite(vals)]
+        if vals.numel() == 0:
+            raise ValueError("sigma' could not be evaluated anywhere on the domain lattice")
+        return 1.05 * float(vals.abs().max())
 
     def _sigma_prime_lattice_vectorised(self, n):
         (x0, x1), (y0, y1) = [[float(a), float(b)] for a, b in self.domain_bounds]
@@ -242,10 +273,11 @@ class WostSolver_2D:
             sigma = self._dev_field(self.sigma, device) if self._sigma_given else None
             if self.sp_mode == SP_FIELD:
                 sp = self._dev_field(self._sigma_prime_plain, device, self.sigma_prime_resolution)
-            key = ("icdf", float(self.sigma_bar), device)
-            if key not in self._cache:
-                self._cache[key] = torch.from_numpy(screened_radius_icdf(self.sigma_bar)).to(torch.device("cuda", device))
-            icdf = self._cache[key]
+            if self.compat != "physical":                                # physical mode samples the radius directly
+                key = ("icdf", float(self.sigma_bar), device)
+                if key not in self._cache:
+                    self._cache[key] = torch.from_numpy(screened_radius_icdf(self.sigma_bar)).to(torch.device("cuda", device))
+                icdf = self._cache[key]
         fields = nat.fields_struct(g=g, f=f, alpha=alpha, sigma=sigma, sigma_prime=sp)
         keep = (g, f, alpha, sigma, sp)
         return self._scene(device), fields, icdf, keep

@@ -85,11 +85,14 @@ enum {
 /* which estimator wost_solve runs */
 enum {
     WOST_COMPAT_REFERENCE = 0,  /* the reference's walk, quirks included — the parity mode                   */
-    WOST_COMPAT_PHYSICAL = 1    /* textbook Walk on Stars for constant coefficients (no delta tracking): hits by true ray   */
-                                /* distance, reflection into the hemisphere facing the domain, closing vertex of closed     */
-                                /* loops is a silhouette candidate, termination projects onto the Dirichlet boundary,       */
-                                /* source radius from the disc Green's function with an independent direction, visibility   */
-                                /* tested.  Not in the reference; validated against analytic mixed-boundary solutions.      */
+    WOST_COMPAT_PHYSICAL = 1    /* textbook Walk on Stars: hits by true ray distance, reflection into the hemisphere facing */
+                                /* the domain, closing vertex of closed loops is a silhouette candidate, termination        */
+                                /* projects onto the Dirichlet boundary, source radius from the disc Green's function with   */
+                                /* an independent direction, visibility tested.  With delta_tracking: variable coefficients  */
+                                /* through U = sqrt(alpha) u and the screened ball kernel's own weights; sigma_bar must be a */
+                                /* true majorant of |sigma'|, steps are capped at 1/sqrt(sigma_bar), screened_icdf is not    */
+                                /* used, Neumann walls need d(alpha)/dn = 0.  Not in the reference; validated against        */
+                                /* analytic solutions.                                                                      */
 };
 
 typedef struct {

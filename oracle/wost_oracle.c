@@ -657,12 +657,106 @@ static float run_walk_physical(const orc_params_t* p, walk_rng_t* g, float x0, f
     return total;
 }
 
+/* ---- physical mode with variable coefficients (delta tracking done by the book; not in the reference) -------------
+ * -div(alpha grad u) + sigma u = f.  With U = sqrt(alpha) u:  lap U - sigma' U = -f / sqrt(alpha)  (sigma' as in
+ * WoStSolver.py:88-121), rewritten with a majorant sigma_bar:  lap U - sigma_bar U = -[f / sqrt(alpha) + (sigma_bar - sigma') U].
+ * On the star-shaped region St(x, r) with the ball's screened Green's function G (zero on the sphere, zero-Neumann walls):
+ *     U(x) = int_{dSt} P U + int_{St} G [f / sqrt(alpha) + (sigma_bar - sigma') U],
+ * estimated with one sample per step: a direction e (first hit at distance t <= r: sphere or wall) and a volume point
+ * y = x + rho e2 with rho ~ 4 rho ln(r / rho) / r^2 (the Laplace Green's density; the screened one is G = ratio(rho) * G0).
+ *   - source:   w * ratio(rho) * r^2/4 * f(y) / sqrt(alpha(y))                      if y is visible from x
+ *   - with probability p_v = 1 - 1/I0(c), c = r sqrt(sigma_bar): continue from y with
+ *                w *= ratio(rho) * (c^2/4) / p_v * (1 - sigma'(y) / sigma_bar)      (w = 0 if y is not visible)
+ *   - else continue from the hit point with  w *= 2 pi Q(t) I0(c)  (= 1 on the sphere, in [1, I0(c)] on a wall), where
+ *                2 pi Q(t) = c_t [K1(c_t) + K0(c) I1(c_t) / I0(c)],  c_t = t sqrt(sigma_bar)  is the flux of G through dSt.
+ * The radius is capped at 1/sqrt(sigma_bar) so c <= 1 and all weights stay near 1.  Walls must have d(alpha)/dn = 0
+ * (otherwise the transformed problem has a Robin condition there).  Bessel functions in double, by quadrature / series. */
+static double orc_i1(double z) {
+    double q = 0.25 * z * z, term = 1.0, sum = 1.0;
+    for (int k = 1; k < 500; ++k) { term *= q / ((double)k * (double)(k + 1)); sum += term; if (term < 1e-17 * sum) break; }
+    return 0.5 * z * sum;
+}
+/* K1(z) = int_0^inf exp(-z cosh t) cosh t dt, trapezoid rule like orc_k0 */
+double orc_k1(double z) {
+    if (z <= 0.0) return INFINITY;
+    const double h = 0.0625; double sum = 0.5 * exp(-z);
+    for (int k = 1; k < 8000; ++k) { double ch = cosh(k * h), a = z * ch; if (a > 745.0) break; sum += exp(-a) * ch; }
+    return h * sum;
+}
+/* G_screened(rho; r) / G_laplace(rho; r) */
+double orc_phys_green_ratio(double rho, double r, double sb) {
+    double s = sqrt(sb), L = log(r / rho);
+    if (!(L > 1e-7)) return 1.0 / orc_i0(r * s);
+    return (orc_k0(rho * s) - (orc_k0(r * s) / orc_i0(r * s)) * orc_i0(rho * s)) / L;
+}
+/* 2 pi Q(t) I0(c): weight of a wall hit at distance t inside a ball of radius r */
+double orc_phys_wall_weight(double t, double r, double sb) {
+    double s = sqrt(sb), ct = t * s, c = r * s;
+    if (ct <= 0.0) return orc_i0(c);
+    if (ct > c) ct = c;
+    return ct * (orc_k1(ct) * orc_i0(c) + orc_k0(c) * orc_i1(ct));
+}
+
+static float run_walk_physical_delta(const orc_params_t* p, walk_rng_t* g, float x0, float y0, uint32_t pidx, uint32_t widx,
+                                     int32_t* n_steps, int32_t trace_cap, float* trace, int32_t* trace_len) {
+    const int has_neu = p->neu_pts && p->n_neu > 0, has_src = p->f != NULL;
+    const float rmin = (float)((double)p->eps / 2.0), eps = p->eps, rcap = 1.0f / sqrtf(p->sigma_bar);
+    float x = x0, y = y0, total = 0.0f, phi_in = 0.0f, cx = x0, cy = y0, dD;
+    float w = 1.0f / sqrtf(alpha_at(p, x0, y0));
+    int onB = 0, steps = 0;
+    uint32_t o2[4];
+    for (;;) {
+        dD = phys_distance(p->dir_pts, p->n_dir, x, y, &cx, &cy);
+        if (!(steps < p->max_steps && dD > eps && w != 0.0f)) break;
+        float dN = has_neu ? phys_silhouette_distance(p->neu_pts, p->n_neu, x, y) : INFINITY;
+        float m = dN < dD ? dN : dD; m = m < rcap ? m : rcap;
+        float r = m > rmin ? m : rmin;
+        if (trace && steps < trace_cap) { float* t = trace + 4 * steps; t[0] = x; t[1] = y; t[2] = dD; t[3] = dN; }
+        orc_philox4x32_10(pidx, widx, (uint32_t)steps, 2u, g->k0, g->k1, g->o);
+        orc_philox4x32_10(pidx, widx, (uint32_t)steps, 3u, g->k0, g->k1, o2);
+        float theta = onB ? phi_in + (u24(g->o[0]) - 0.5f) * 3.14159274101257324f : (u24(g->o[0]) * 2.0f) * 3.14159274101257324f;
+        float ex = cosf(theta), ey = sinf(theta);
+        float th2 = onB ? phi_in + (u24(g->o[1]) - 0.5f) * 3.14159274101257324f : (u24(g->o[1]) * 2.0f) * 3.14159274101257324f;
+        float sx_ = cosf(th2), sy_ = sinf(th2);
+        float rho = r * sqrtf(u24p(g->o[2]) * u24p(g->o[3]));
+        float th; int vis = 1;
+        if (has_neu) vis = phys_ray(p->neu_pts, p->n_neu, x, y, sx_, sy_, rho, &th) < 0;
+        const float yx = x + rho * sx_, yy = y + rho * sy_;
+        const float ratio = (float)orc_phys_green_ratio((double)rho, (double)r, (double)p->sigma_bar);
+        if (has_src && vis) total += w * (orc_field_eval(p->f, yx, yy) * (ratio * (r * r / 4.0f)) / sqrtf(alpha_at(p, yx, yy)));
+        const double c = (double)r * sqrt((double)p->sigma_bar), i0c = orc_i0(c), pv = i0_minus_1(c) / i0c;
+        if ((double)u24(o2[0]) < pv) {                                       /* null-collision inside the star */
+            if (!vis) w = 0.0f;
+            else {
+                const float sp = orc_sigma_prime(p, yx, yy);
+                w = (w * (ratio * (float)(0.25 * c * c / pv))) * (1.0f - sp / p->sigma_bar);
+                x = yx; y = yy; onB = 0;
+            }
+        } else {
+            float t_hit; int k = has_neu ? phys_ray(p->neu_pts, p->n_neu, x, y, ex, ey, r + p->phys_nudge, &t_hit) : -1;
+            if (k >= 0) {
+                float ux = p->neu_pts[2 * k + 2] - p->neu_pts[2 * k], uy = p->neu_pts[2 * k + 3] - p->neu_pts[2 * k + 1];
+                float len = norm2f(ux, uy), nx = -uy / len, ny = ux / len;
+                if (nx * ex + ny * ey > 0.0f) { nx = -nx; ny = -ny; }
+                w = w * (float)orc_phys_wall_weight((double)t_hit, (double)r, (double)p->sigma_bar);
+                x = (x + t_hit * ex) + p->phys_nudge * nx; y = (y + t_hit * ey) + p->phys_nudge * ny;
+                phi_in = atan2f(ny, nx); onB = 1;
+            } else { x = x + r * ex; y = y + r * ey; onB = 0; }
+        }
+        ++steps;
+    }
+    if (p->g) total += w * (orc_field_eval(p->g, cx, cy) * sqrtf(alpha_at(p, cx, cy)));
+    *n_steps = steps;
+    if (trace_len) *trace_len = steps < trace_cap ? steps : trace_cap;
+    return total;
+}
+
 int orc_solve(const orc_params_t* p, const float* pts, int64_t n_pts,
               double* mean, double* m2, float* walk_vals, int64_t* steps_total, int32_t* walk_steps,
               int64_t n_trace, int32_t trace_cap, float* trace, int32_t* trace_len) {
     const int64_t W = p->n_walks;
     int64_t steps_sum = 0;
-    if (p->compat_mode == 1 && (p->rng_mode != ORC_RNG_PHILOX || p->delta)) return -1;   /* physical: Philox, constant coefficients */
+    if (p->compat_mode == 1 && (p->rng_mode != ORC_RNG_PHILOX || (p->delta && !(p->sigma_bar > 0.0f)))) return -1;   /* physical: Philox only */
     if (p->rng_mode == ORC_RNG_MT) {
         /* one sequential stream over all points and walks, like the reference */
         mt_t torch_rng, np_rng; mt_seed(&torch_rng, (uint32_t)p->seed); mt_seed(&np_rng, (uint32_t)p->seed_numpy);
@@ -703,7 +797,9 @@ int orc_solve(const orc_params_t* p, const float* pts, int64_t n_pts,
                 int64_t flat = pi * W + w; int32_t ns;
                 float* tr = (trace && flat < n_trace) ? trace + (size_t)flat * trace_cap * 4 : NULL;
                 int32_t* tl = (trace_len && flat < n_trace) ? trace_len + flat : NULL;
-                float v = p->compat_mode == 1
+                float v = p->compat_mode == 1 && p->delta
+                    ? run_walk_physical_delta(p, &g, pts[2 * pi], pts[2 * pi + 1], (uint32_t)(p->point_index_base + pi), (uint32_t)(p->walk_offset + w), &ns, trace_cap, tr, tl)
+                    : p->compat_mode == 1
                     ? run_walk_physical(p, &g, pts[2 * pi], pts[2 * pi + 1], (uint32_t)(p->point_index_base + pi), (uint32_t)(p->walk_offset + w), &ns, trace_cap, tr, tl)
                     : run_walk(p, &g, pts[2 * pi], pts[2 * pi + 1], (uint32_t)(p->point_index_base + pi), (uint32_t)(p->walk_offset + w), NULL, &ns, trace_cap, tr, tl);
                 vals[w] = v; if (walk_steps) walk_steps[flat] = ns;

@@ -207,3 +207,53 @@ def test_physical_mode_matches_analytic_mixed_boundary_solutions(key):
     ref = orc.Problem.from_scenario(s).solve(s.points, nw, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=11, compat="reference")
     zr = np.abs(ref["mean"] - exact) / (ref["stderr"] + slack)
     assert not np.all(np.isfinite(zr)) or np.max(zr) > 5.0
+
+
+def test_physical_delta_weights_against_scipy():
+    """K1 quadrature, G_screened / G_laplace and the wall-hit weight 2 pi Q(t) I0(c) of the physical variable-coefficient walk."""
+    import ctypes as C
+    from scipy import special as sp
+
+    L = orc.lib()
+    for fn, n in ((L.orc_k1, 1), (L.orc_phys_green_ratio, 3), (L.orc_phys_wall_weight, 3)):
+        fn.restype, fn.argtypes = C.c_double, [C.c_double] * n
+    for z in (1e-5, 1e-2, 0.5, 1.0, 2.0, 7.0):
+        assert abs(L.orc_k1(z) / sp.k1(z) - 1.0) < 1e-12
+    rng = np.random.default_rng(0)
+    for r, sb in ((0.5, 3.0), (0.05, 1.7), (1.0, 1.0)):
+        c, s = r * np.sqrt(sb), np.sqrt(sb)
+        rho = r * np.sqrt(rng.random(2000) * rng.random(2000))
+        ratio = np.array([L.orc_phys_green_ratio(x, r, sb) for x in rho])
+        exact = (sp.k0(rho * s) - sp.k0(c) / sp.i0(c) * sp.i0(rho * s)) / np.log(r / rho)
+        assert np.allclose(ratio, exact, rtol=1e-9)
+        assert np.all(ratio <= 1.0 + 1e-12) and np.all(ratio >= 1.0 / sp.i0(c) - 1e-9)      # screening only removes mass
+        t = r * rng.random(200)
+        w = np.array([L.orc_phys_wall_weight(x, r, sb) for x in t])
+        assert np.allclose(w, t * s * (sp.k1(t * s) * sp.i0(c) + sp.k0(c) * sp.i1(t * s)), rtol=1e-9)
+        assert np.all(w >= 1.0 - 1e-12) and np.all(w <= sp.i0(c) + 1e-12)
+        assert abs(L.orc_phys_wall_weight(r, r, sb) - 1.0) < 1e-12                           # Wronskian: the sphere weighs 1
+    # E_{rho ~ Laplace density}[ratio] = |G_screened| / |G_laplace|
+    r, sb = 0.5, 3.0
+    c = r * np.sqrt(sb)
+    rho = r * np.sqrt(rng.random(200000) * rng.random(200000))
+    m = np.mean([L.orc_phys_green_ratio(x, r, sb) for x in rho[:20000]])
+    assert abs(m - (1 - 1 / sp.i0(c)) / (c * c / 4)) < 2e-3
+
+
+@pytest.mark.parametrize("key", sorted(sc.PHYSICAL_VARCOEF))
+def test_physical_mode_with_variable_coefficients_converges_to_analytic(key):
+    """Delta tracking by the book converges where the reference's estimator has a bias floor (cfg 1b: RMSE 0.028)."""
+    s = sc.PHYSICAL_VARCOEF[key]()
+    solver = s.make_solver()                                             # host setup only: sigma', the majorant
+    assert solver.use_delta_tracking and solver.sigma_bar > 0
+    nw = 30000
+    r = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar).solve(s.points, nw, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX,
+                                                                      seed=11, compat="physical")
+    exact = s.analytic(s.points).numpy()
+    z = np.abs(r["mean"] - exact) / (r["stderr"] + 3e-4)
+    assert np.all(z <= 3.6), z
+    assert np.sqrt(np.mean((r["mean"] - exact) ** 2)) < 8e-3
+    if key == "phys_varcoef_dirichlet":
+        ref = sc.cfg1b()
+        rr = orc.Problem.from_scenario(ref).solve(ref.points, nw, ref.max_steps, ref.eps, rng_mode=orc.RNG_PHILOX, seed=11)
+        assert np.sqrt(np.mean((rr["mean"] - exact) ** 2)) > 0.02        # the reference's bias floor
