@@ -149,7 +149,11 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             const int rank = __popc(need & lt_mask);
             if (mine && (unsigned long long)rank < avail) {
                 id = next + (unsigned long long)rank;
-                const unsigned long long p = id / (unsigned long long)a.n_walks, w = id - p * (unsigned long long)a.n_walks;
+                unsigned long long p, w;
+                if (total <= 0xffffffffull) {                          // the usual case: 32-bit division
+                    const uint32_t p32 = (uint32_t)id / (uint32_t)a.n_walks;
+                    p = p32; w = (uint32_t)id - p32 * (uint32_t)a.n_walks;
+                } else { p = id / (unsigned long long)a.n_walks; w = id - p * (unsigned long long)a.n_walks; }
                 pidx = (uint32_t)(a.point_index_base + (long long)p); widx = (uint32_t)(a.walk_offset + (long long)w);
                 x = __ldg(a.pts + 2 * p); y = __ldg(a.pts + 2 * p + 1);
                 dD = 1.0f;                                             // :190 sentinel (Q6)
@@ -162,7 +166,11 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             next += cnt < avail ? cnt : avail;
             need = __ballot_sync(FULL, !active && !retired);
         }
-        if (__ballot_sync(FULL, active) == 0u) break;
+        // Dirichlet-only delta-tracking kernels are instruction-fetch bound (ncu: a third of the stall samples are
+        // no_instruction); one CTA barrier per iteration keeps the warps in the same code region: +5 % there, a loss
+        // for the kernels with cooperative Neumann loops (iteration times differ per warp), so only there.
+        if (!NEU && DELTA && !PHYS) { if (!__syncthreads_or(active ? 1 : 0)) break; }
+        else if (__ballot_sync(FULL, active) == 0u) break;
 
         // ---- this iteration: every active lane either takes one step of the reference's loop or terminates ----
         // reference: the loop condition tests the PREVIOUS step's dDirichlet (:206, Q5).
@@ -300,14 +308,30 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 } else if (want_ray) bvh_ray_cast<PHYS>(a.nseg, a.n_nseg, a.nbvh, a.bvh_slack, ox, oy, ex, ey, best_s, best_k);
             } else if (__popc(need) > a.ray_coop_max) {
                 if (want_ray) ray_cast<PHYS>(nseg, a.n_nseg, ox, oy, ex, ey, best_s, best_k);
+            } else if (small) {
+                // one segment per lane: the warp runs the division-free prefilter for each ray in turn and hands the
+                // ray's owner the mask of candidate segments; afterwards all owners resolve their (one or two)
+                // candidates at the same time with the reference's exact arithmetic, in index order (first index wins ties)
+                unsigned cand = 0u;
+                while (need) {
+                    const int src = __ffs(need) - 1; need &= need - 1u;
+                    const float rox = __shfl_sync(FULL, ox, src), roy = __shfl_sync(FULL, oy, src);
+                    const float rex = __shfl_sync(FULL, ex, src), rey = __shfl_sync(FULL, ey, src);
+                    const unsigned b = __ballot_sync(FULL, lane < a.n_nseg && ray_segment_candidate(nseg0, rox, roy, rex, rey));
+                    cand = lane == src ? b : cand;
+                }
+                while (cand) {
+                    const int k = __ffs(cand) - 1; cand &= cand - 1u;
+                    const float s = ray_segment_exact<PHYS>(nseg[2 * k], ox, oy, ex, ey);
+                    if (s < best_s) { best_s = s; best_k = k; }
+                }
             } else {
                 while (need) {
                     const int src = __ffs(need) - 1; need &= need - 1u;
                     const float rox = __shfl_sync(FULL, ox, src), roy = __shfl_sync(FULL, oy, src);
                     const float rex = __shfl_sync(FULL, ex, src), rey = __shfl_sync(FULL, ey, src);
                     float cs; int ck;
-                    if (small) ray_cast_coop<true, PHYS>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
-                    else ray_cast_coop<false, PHYS>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
+                    ray_cast_coop<false, PHYS>(nseg, a.n_nseg, nseg0, rox, roy, rex, rey, lane, cs, ck);
                     best_s = lane == src ? cs : best_s; best_k = lane == src ? ck : best_k;
                 }
             }
@@ -1228,6 +1252,8 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
         a.ray_coop_max = n >= 8 ? (20 * n) / (16 * chunks + 14) : 0;
         if (a.sil_coop_max > 32) a.sil_coop_max = 32;
         if (a.ray_coop_max > 32) a.ray_coop_max = 32;
+        a.sil_coop_max = env_int("WOST_SIL_COOP_MAX", a.sil_coop_max);
+        a.ray_coop_max = env_int("WOST_RAY_COOP_MAX", a.ray_coop_max);
     }
     a.dbvh.nodes = scene->dbvh; a.dbvh.n_leaves = scene->dbvh_leaves; a.nbvh.nodes = scene->nbvh; a.nbvh.cones = scene->ncones; a.nbvh.n_leaves = scene->nbvh_leaves;
     a.dwide = scene->dwide; a.nwide = scene->nwide; a.wide_coop_max = env_int("WOST_WIDE_COOP_MAX", 20);
