@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 }
             }
             if (PHYS && a.neu_closed && want_sil) dN2 = fminf(dN2, closing_vertex_silhouette_sq(a.nseg, a.n_nseg, x, y));
-            dN = sqrtf(dN2);
+            dN = dN2 == CUDART_INF_F ? CUDART_INF_F : sqrtf(dN2);           // no silhouette vertex: spare sqrt its special-value path
             need = __ballot_sync(FULL, want_ray);                                       // ray vs polyline (:162-178)
             if (BIG && a.nbvh.nodes) {
                 if (a.nwide.boxes && __popc(need) <= a.wide_coop_max) {
@@ -479,11 +479,11 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                             const float4 sup = __ldg(a.src_support + k);
                             if ((sx - sup.x) * (sx - sup.x) + (sy - sup.y) * (sy - sup.y) > sup.z) continue;   // exactly zero there
                             const float fk = field_eval(a.srcs[k], sx, sy);
-                            if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);
+                            if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);   // fk != 0: plain division
                         }
                     } else if (DELTA) {                                                 // :252-254
                         alpha_s = alpha_at(a.F, sx, sy); have_alpha_s = true;
-                        contrib = (field_eval(a.F.f, sx, sy) * gn / sqrtf(alpha_s * alpha_x)) * atten;
+                        contrib = div_z(field_eval(a.F.f, sx, sy) * gn, sqrtf(alpha_s * alpha_x)) * atten;
                     } else
                         contrib = field_eval_inl(a.F.f, sx, sy) * (r * r / 4.0f);       // :256
                 }
@@ -1082,7 +1082,17 @@ int wost_field_create(const wost_field_desc_t* d, int32_t device, wost_field_t**
     cudaError_t e = cudaSuccess;
     if (D.n_terms > 0) {
         e = cudaMalloc((void**)&f->terms, sizeof(wost_term_t) * D.n_terms);
-        if (e == cudaSuccess) e = cudaMemcpy(f->terms, d->terms, sizeof(wost_term_t) * D.n_terms, cudaMemcpyHostToDevice);
+        // the device copy of a smooth-circle term carries the squared radii beyond which the step is exactly 0 / 1
+        // in its (otherwise unused) w1x / w1y slots: same fp32 expressions as the oracle evaluates per call
+        std::vector<wost_term_t> terms(d->terms, d->terms + D.n_terms);
+        for (auto& t : terms)
+            if (t.kind == WOST_TERM_SIGMOID_CIRCLE) {
+                const float ro = t.R + 88.0f / t.q, ri = t.R - 18.0f / t.q;
+                const float ro2 = ro * ro, ri2 = ri * ri;
+                t.w1x = ro2 * 1.0001f;
+                t.w1y = ri > 0.0f ? ri2 * 0.9999f : -1.0f;
+            }
+        if (e == cudaSuccess) e = cudaMemcpy(f->terms, terms.data(), sizeof(wost_term_t) * D.n_terms, cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess && d->kind == WOST_FIELD_GRID) {
         const size_t n = (size_t)d->nx * d->ny;

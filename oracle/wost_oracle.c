@@ -472,8 +472,8 @@ static void greens_norm_pair(const orc_params_t* p, float r, int r_is_rmin, doub
         }
     } else {
         float zf = r * (float)sqrt(sb);
-        double m1 = i0_minus_1((double)zf);
-        double Q = m1 / (1.0 + m1);                                  /* 1 - 1/I0 without cancellation */
+        double m1 = zf > 21.0f ? 0.0 : i0_minus_1((double)zf);
+        double Q = zf > 21.0f ? 1.0 : m1 / (1.0 + m1);               /* 1 - 1/I0 without cancellation; 1 to fp32 beyond z = 21 (and no inf/inf) */
         *sbgn = (float)Q; *gn = (float)(Q / sb);
     }
 }
