@@ -66,6 +66,7 @@ struct WalkArgs {
     int stage_smem;                        // bit 0 / 1: Dirichlet / Neumann segment table is staged in shared memory
     DevFields F;
     const float* pts; long long n_pts; long long n_walks;
+    const float* alpha0;                   // delta tracking: alpha at every evaluation point (all walks of a point start there)
     int max_steps; float eps, rmin;
     int sp_mode; float sigma_bar, inv_sigma_bar, sqrt_sigma_bar;
     const float* icdf; int icdf_len;
@@ -112,6 +113,10 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         }
         if (a.stage_smem) __syncthreads();
     }
+    // Terminated walks are parked here (where g is read, the walk's weight and running total, its index) and their
+    // boundary term is evaluated later for many lanes at once: evaluated on the spot, g would run with the one or two
+    // lanes that happen to terminate in an iteration (ncu, cfg 4: 18 % of all instructions at 2 of 32 lanes).
+    __shared__ float4 parked[2 * 256];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -120,6 +125,8 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
     // warp-uniform reservation [next, end)
     unsigned long long next = 0, end = 0;
     bool exhausted = false;
+    unsigned parked_mask = 0u;                 // warp-uniform: lanes with a parked walk
+    bool flush_now = false;                    // warp-uniform: a lane terminated again while still parked
 
     // per-lane walk state
     bool active = false, retired = false;
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 x = __ldg(a.pts + 2 * p); y = __ldg(a.pts + 2 * p + 1);
                 dD = 1.0f;                                             // :190 sentinel (Q6)
                 atten = 1.0f; total_v = 0.0f; onB = false; phi_n = 0.0f; steps = 0;   // :188-195
-                if (DELTA) alpha_x = alpha_at(a.F, x, y);
+                if (DELTA) alpha_x = __ldg(a.alpha0 + p);                // = alpha_at(a.F, x, y), evaluated once per point
                 if (PHYS && DELTA) atten = 1.0f / sqrtf(alpha_x);          // u = U / sqrt(alpha): the walk estimates U
                 active = true;
             }
@@ -169,8 +176,37 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         // Dirichlet-only delta-tracking kernels are instruction-fetch bound (ncu: a third of the stall samples are
         // no_instruction); one CTA barrier per iteration keeps the warps in the same code region: +5 % there, a loss
         // for the kernels with cooperative Neumann loops (iteration times differ per warp), so only there.
-        if (!NEU && DELTA && !PHYS) { if (!__syncthreads_or(active ? 1 : 0)) break; }
-        else if (__ballot_sync(FULL, active) == 0u) break;
+        bool none;
+        if (!NEU && DELTA && !PHYS) none = !__syncthreads_or(active ? 1 : 0);
+        else none = __ballot_sync(FULL, active) == 0u;
+
+        // ---- boundary terms of the parked walks (:295-298), all parked lanes together ----------------------------------
+        if ((flush_now || none) && parked_mask) {
+            if ((parked_mask >> lane) & 1u) {
+                const float4 p0 = parked[threadIdx.x], p1 = parked[256 + threadIdx.x];
+                const float gx_ = p0.x, gy_ = p0.y, w_ = p0.z, tot_ = p0.w;
+                const unsigned long long pid = ((unsigned long long)__float_as_uint(p1.y) << 32) | __float_as_uint(p1.x);
+                float bc = 0.0f;
+                if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, gx_, gy_) : field_eval_inl(a.F.g, gx_, gy_);
+                if (PHYS && DELTA) bc = w_ * (bc * sqrtf(alpha_at(a.F, gx_, gy_)));   // U = sqrt(alpha) g on the boundary
+                else if (DELTA) bc = bc * w_;
+                if (SRC && a.n_src > 0) {                                     // one total per source: same walk, same boundary term
+                    float* row = a.walk_vals + (size_t)pid * a.n_src;
+                    for (int k = 0; k < a.n_src; ++k) row[k] = row[k] + bc;
+                } else a.walk_vals[pid] = tot_ + bc;
+                if (TRACE) {
+                    if ((long long)pid < a.n_trace) {                         // terminal row: where g was read, what it contributed
+                        const int nst = __float_as_int(p1.z), len = min(nst, a.trace_cap);
+                        a.trace_len[pid] = len;
+                        float4* t = reinterpret_cast<float4*>(a.trace) + ((size_t)pid * (a.trace_cap + 1) + len) * 2;
+                        t[0] = make_float4(gx_, gy_, bc, tot_ + bc); t[1] = make_float4((float)nst, 0.0f, 0.0f, 1.0f);
+                    }
+                }
+            }
+            parked_mask = 0u;
+        }
+        flush_now = false;
+        if (none) break;
 
         // ---- this iteration: every active lane either takes one step of the reference's loop or terminates ----
         // reference: the loop condition tests the PREVIOUS step's dDirichlet (:206, Q5).
@@ -179,28 +215,30 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         if (PHYS && active)
             dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, a.n_dseg, a.dbvh, x, y, &dir_arg) : dirichlet_distance(dseg, a.n_dseg, x, y, &dir_arg);
         const bool stepping = active && steps < a.max_steps && dD > a.eps && !(PHYS && DELTA && atten == 0.0f);   // weight 0: absorbed
-        if (active && !stepping) {
-            // terminal: boundary contribution at the un-projected point (:295-298, Q5/Q7)
-            float gx_ = x, gy_ = y;
-            if (PHYS && dir_arg >= 0) segment_closest_point(a.dseg[2 * dir_arg], a.dseg[2 * dir_arg + 1], x, y, gx_, gy_);
-            float bc = 0.0f;
-            if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, gx_, gy_) : field_eval_inl(a.F.g, gx_, gy_);
-            if (PHYS && DELTA) bc = atten * (bc * sqrtf(alpha_at(a.F, gx_, gy_)));   // U = sqrt(alpha) g on the boundary
-            else if (DELTA) bc = bc * atten;
-            if (SRC && a.n_src > 0) {                                     // one total per source: same walk, same boundary term
-                float* row = a.walk_vals + (size_t)id * a.n_src;
-                for (int k = 0; k < a.n_src; ++k) row[k] = row[k] + bc;
-            } else a.walk_vals[id] = total_v + bc;
-            if (TRACE) {
-                if ((long long)id < a.n_trace) {                          // terminal row: where g was read, what it contributed
-                    const int len = min(steps, a.trace_cap);
-                    a.trace_len[id] = len;
-                    float4* t = reinterpret_cast<float4*>(a.trace) + ((size_t)id * (a.trace_cap + 1) + len) * 2;
-                    t[0] = make_float4(gx_, gy_, bc, total_v + bc); t[1] = make_float4((float)steps, 0.0f, 0.0f, 1.0f);
+        {
+            // terminal: the boundary contribution is read at the un-projected point (:295-298, Q5/Q7); park the walk.
+            // A lane whose previous walk is still parked waits one iteration: the parked walks are resolved first.
+            const bool term = active && !stepping;
+            const unsigned tmask = __ballot_sync(FULL, term);
+            if (!TRACE && !a.F.g.present && !(SRC && a.n_src > 0)) {        // g = 0: nothing to evaluate, nothing to park
+                if (term) {
+                    a.walk_vals[id] = total_v + (DELTA ? 0.0f * atten : 0.0f);
+                    steps_acc += (unsigned long long)steps;
+                    active = false;
                 }
+            } else if (tmask) {
+                const unsigned conflict = tmask & parked_mask;
+                if (term && !((parked_mask >> lane) & 1u)) {
+                    float gx_ = x, gy_ = y;
+                    if (PHYS && dir_arg >= 0) segment_closest_point(a.dseg[2 * dir_arg], a.dseg[2 * dir_arg + 1], x, y, gx_, gy_);
+                    parked[threadIdx.x] = make_float4(gx_, gy_, atten, total_v);
+                    parked[256 + threadIdx.x] = make_float4(__uint_as_float((unsigned)id), __uint_as_float((unsigned)(id >> 32)), __int_as_float(steps), 0.0f);
+                    steps_acc += (unsigned long long)steps;
+                    active = false;
+                }
+                parked_mask |= tmask & ~conflict;
+                flush_now = conflict != 0u;
             }
-            steps_acc += (unsigned long long)steps;
-            active = false;
         }
 
         // very large Dirichlet polylines: the distance query of every stepping lane, one warp-cooperative descent each
@@ -656,6 +694,12 @@ __global__ void field_eval_kernel(DevField F, const float* p, long long B, float
         if (gy) gy[i] = j.gy;
         if (lap) lap[i] = j.l;
     }
+}
+
+// alpha at the evaluation points, for the walk kernel's regeneration (there only a lane or two start a walk per iteration)
+__global__ void alpha0_kernel(DevFields F, const float* p, long long B, float* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) out[i] = alpha_at(F, p[2 * i], p[2 * i + 1]);
 }
 
 __global__ void sigma_prime_kernel(DevFields F, int sp_mode, const float* p, long long B, float* out) {
@@ -1233,6 +1277,8 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     }
     unsigned long long* ctrs = nullptr;
     CU(cudaMallocAsync((void**)&ctrs, 2 * sizeof(unsigned long long), st));
+    float* alpha0 = nullptr;
+    if (delta) CU(cudaMallocAsync((void**)&alpha0, sizeof(float) * (size_t)n_pts, st));
     CU(cudaMemsetAsync(ctrs, 0, 2 * sizeof(unsigned long long), st));
     double* blk = s_blk.dev; bool blk_temp = false;
     if (!blk) { CU(cudaMallocAsync((void**)&blk, sizeof(double) * 2 * n_pts * nblk * S, st)); blk_temp = true; }
@@ -1245,6 +1291,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.dseg = scene->dseg; a.n_dseg = scene->n_dseg; a.nseg = scene->nseg; a.n_nseg = scene->n_nseg;
     a.F = dev_fields_of(fields);
     a.n_src = n_sources; a.srcs = d_srcs; a.src_support = d_sup;
+    if (alpha0) { alpha0_kernel<<<blocks_for(n_pts, 256), 256, 0, st>>>(a.F, s_pts.dev, n_pts, alpha0); CU(cudaGetLastError()); }
     a.pts = s_pts.dev; a.n_pts = n_pts; a.n_walks = W;
     a.max_steps = P->max_steps; a.eps = P->eps; a.rmin = (float)((double)P->eps / 2.0);   // :167
     a.sp_mode = P->sp_mode; a.sigma_bar = P->sigma_bar;
@@ -1296,6 +1343,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
         if (total < nwarps * 32) a.chunk = (int)((total + nwarps - 1) / nwarps);
         if (a.chunk < 1) a.chunk = 1;
         a.pts = s_pts.dev + 2 * p0; a.n_pts = np; a.point_index_base = P->point_index_base + p0;
+        a.alpha0 = alpha0 ? alpha0 + p0 : nullptr;
         a.walk_vals = vals_dev_out ? out_walk_vals + (size_t)p0 * W : vals;
         if (trace) {                                                    // the first n_trace walks in point-major order
             const long long first = p0 * W;
@@ -1328,6 +1376,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (d_sup) CU(cudaFreeAsync(d_sup, st));
     if (blk_temp) CU(cudaFreeAsync(blk, st));
     CU(cudaFreeAsync(ctrs, st));
+    if (alpha0) CU(cudaFreeAsync(alpha0, st));
     if (sync) CU(cudaStreamSynchronize(st));
     return WOST_OK;
 }
