@@ -47,7 +47,8 @@ class SolveParams(C.Structure):
     _fields_ = [("n_walks", C.c_int64), ("max_steps", C.c_int32), ("eps", C.c_float), ("delta_tracking", C.c_int32),
                 ("sp_mode", C.c_int32), ("sigma_bar", C.c_float), ("screened_icdf", C.c_void_p), ("icdf_len", C.c_int32),
                 ("seed", C.c_uint64), ("point_index_base", C.c_int64), ("walk_offset", C.c_int64), ("compat_mode", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("majorant_levels", C.c_int32), ("majorant", C.c_void_p),
+                ("majorant_x0", C.c_float), ("majorant_y0", C.c_float), ("majorant_dx", C.c_float), ("majorant_dy", C.c_float)]
 
 
 EXPORTS = {
@@ -190,10 +191,22 @@ def sigma_prime_eval(fields: Fields, sp_mode: int, pts, device: int):
     return out
 
 
+def _set_majorant(prm, majorant):
+    """majorant: None or dict(data=float32 pyramid (numpy or CUDA tensor), levels, x0, y0, dx, dy) -- see include/wost.h."""
+    if majorant is None:
+        return None
+    data = majorant["data"]
+    keep = data if (isinstance(data, torch.Tensor) and data.is_cuda) else host_f32(data)
+    prm.majorant, prm.majorant_levels = ptr(keep).value, int(majorant["levels"])
+    prm.majorant_x0, prm.majorant_y0 = float(majorant["x0"]), float(majorant["y0"])
+    prm.majorant_dx, prm.majorant_dy = float(majorant["dx"]), float(majorant["dy"])
+    return keep
+
+
 def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: float, *, delta: bool = False,
           sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0, point_index_base: int = 0,
           walk_offset: int = 0, want_block_stats: bool = False, want_walk_vals: bool = False, n_trace: int = 0,
-          trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference"):
+          trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference", majorant=None):
     """One wost_solve call.  ``pts`` may be a host array/tensor or a CUDA tensor on the scene's device.
     With ``device_outputs`` the results stay on the device as torch tensors (stream-ordered, no sync)."""
     dev = scene.device
@@ -212,6 +225,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
     prm.compat_mode = COMPAT[compat]
+    maj_keep = _set_majorant(prm, majorant)
 
     if device_outputs:
         tdev = torch.device("cuda", dev)
@@ -244,7 +258,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
 def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int, max_steps: int, eps: float, *,
                        delta: bool = False, sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0,
                        point_index_base: int = 0, walk_offset: int = 0, want_block_stats: bool = False,
-                       device_outputs: bool = False, compat: str = "reference"):
+                       device_outputs: bool = False, compat: str = "reference", majorant=None):
     """One wost_solve_multi_source call: shared walks, one estimate per (source, point).  ``sources`` is a list of
     DeviceField.  Returns mean / m2 of shape (S, P)."""
     dev = scene.device
@@ -263,6 +277,7 @@ def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int,
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
     prm.compat_mode = COMPAT[compat]
+    maj_keep = _set_majorant(prm, majorant)
     handles = (C.c_void_p * S)(*[s.handle for s in sources])
     if device_outputs:
         tdev = torch.device("cuda", dev)

@@ -82,6 +82,7 @@ struct WalkArgs {
     WideBvh dwide;                         // 32-wide Dirichlet hierarchy: the distance query, one warp per query
     int neu_closed; float phys_nudge;      // physical mode: closed Neumann loop?  pull-back of a reflected walker
     float phys_rcap;                       // physical mode with variable coefficients: step radius cap 1/sqrt(sigma_bar)
+    MajorantPyramid maj;                   // ... or a spatially varying majorant (data == nullptr: sigma_bar everywhere)
     const float4* src_support;             // per source (cx, cy, R^2): exactly zero outside
     int n_src; const DevField* srcs;       // shared-walk multi-source solve: n_src > 0 source fields (device array); per-walk
                                            // totals then form rows walk_vals[walk][n_src]
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
 
         // ---- phase A: Dirichlet distance, direction --------------------------------------------------------------
         float dN = CUDART_INF_F, r = 0.f, dx = 0.f, dy = 0.f, ex = 0.f, ey = 0.f, ox = 0.f, oy = 0.f;
+        float pd_sb = a.sigma_bar;                 // physical delta tracking: the majorant this step uses
         bool want_ray = false, want_sil = false;
         float gap = 0.0f;
         if (stepping) {
@@ -376,8 +378,16 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
         }
         if (stepping) {
             float m = NEU ? (dN < dD ? dN : dD) : dD;                                   // :212 / :215
-            if (PHYS && DELTA) m = m < a.phys_rcap ? m : a.phys_rcap;                   // keeps r sqrt(sigma_bar) <= 1
-            r = (m > a.rmin) ? m : a.rmin;
+            if (PHYS && DELTA) {
+                if (a.maj.data) {                                                       // majorant of this step's ball
+                    float M;
+                    r = majorant_radius(a.maj, x, y, m, a.rmin, M);
+                    pd_sb = fmaxf(M, 1e-8f / (r * r));                                  // sigma' = 0 around here: plain WoSt step
+                } else {
+                    m = m < a.phys_rcap ? m : a.phys_rcap;                              // keeps r sqrt(sigma_bar) <= 1
+                    r = (m > a.rmin) ? m : a.rmin;
+                }
+            } else r = (m > a.rmin) ? m : a.rmin;
         }
 
         // ---- phase C: move, source sample, delta tracking ---------------------------------------------------------
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 float wsrc = r * r / 4.0f;                                              // |G| of the Laplace ball kernel
                 if (DELTA) {
                     // screened ball kernel G = ratio(rho) G_laplace; the source of the transformed equation is f / sqrt(alpha)
-                    const float c = r * a.sqrt_sigma_bar;
+                    const float c = r * sqrtf(pd_sb);
                     float sc;
                     pd_qc = 0.25f * (c * c);
                     bessel_i0m1_s(pd_qc, pd_m1, sc);
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                     if (best_k < 0 || best_s > r + a.phys_nudge) { qx = x + r * ex; qy = y + r * ey; onB = false; }
                     else {
                         if (DELTA && !pd_vol) {                                         // flux of the screened kernel through the wall
-                            const float ct = fminf(best_s, r) * a.sqrt_sigma_bar;
+                            const float ct = fminf(best_s, r) * sqrtf(pd_sb);
                             atten = atten * phys_wall_weight(pd_i0c, pd_k0c, 0.25f * (ct * ct));
                         }
                         // reflect: sit `nudge` off the wall on the side we came from, remember that side's normal
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 if (!pd_vis) { atten = 0.0f; qx = x; qy = y; }                          // the sample fell behind a wall
                 else {
                     const float sp = sigma_prime_at(a.F, a.sp_mode, pd_yx, pd_yy);
-                    atten = (atten * (pd_ratio * (pd_qc * pd_i0c / pd_m1))) * (1.0f - sp / a.sigma_bar);
+                    atten = (atten * (pd_ratio * (pd_qc * pd_i0c / pd_m1))) * (1.0f - sp / pd_sb);
                     qx = pd_yx; qy = pd_yy;
                 }
                 onB = false;
@@ -1245,11 +1255,18 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
         if (!sources[k] || sources[k]->device != scene->device) return fail(WOST_ERR_INVALID, "source field missing or on another device");
     if (n_sources > 0 && (n_trace > 0 || out_walk_vals)) return fail(WOST_ERR_UNSUPPORTED, "trace / per-walk output is not available for multi-source solves");
 
-    Staged<float> s_pts, s_trace, s_icdf; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
+    Staged<float> s_pts, s_trace, s_icdf, s_maj; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
     int rc;
     if ((rc = s_pts.init(pts_xy, 2 * n_pts, false, st))) return rc;
     const bool use_icdf = delta && !phys_delta;
     if ((rc = s_icdf.init(use_icdf ? P->screened_icdf : nullptr, use_icdf ? P->icdf_len : 0, false, st))) return rc;
+    size_t maj_len = 0;
+    if (phys_delta && P->majorant_levels > 0) {
+        if (P->majorant_levels > 13 || !P->majorant || !(P->majorant_dx > 0.0f) || !(P->majorant_dy > 0.0f))
+            return fail(WOST_ERR_INVALID, "majorant pyramid: 1..13 levels, data and positive cell sizes needed");
+        for (int l = 0, n = 1 << (P->majorant_levels - 1); l < P->majorant_levels; ++l, n >>= 1) maj_len += (size_t)n * n;
+    }
+    if ((rc = s_maj.init(maj_len ? P->majorant : nullptr, maj_len, false, st))) return rc;
     if ((rc = s_mean.init(out_mean, (size_t)S * n_pts, true, st)) || (rc = s_m2.init(out_m2, (size_t)S * n_pts, true, st)) ||
         (rc = s_blk.init(out_block_stats, (size_t)S * 2 * n_pts * nblk, true, st)) || (rc = s_steps.init(out_steps, 1, true, st)) ||
         (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * (trace_cap + 1) * 8 : 0, true, st)) ||
@@ -1316,6 +1333,8 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.dwide = scene->dwide; a.nwide = scene->nwide; a.wide_coop_max = env_int("WOST_WIDE_COOP_MAX", 20);
     a.bvh_slack = scene->bvh_slack; a.neu_closed = scene->neu_closed; a.phys_nudge = scene->phys_nudge;
     a.phys_rcap = phys_delta ? 1.0f / sqrtf(P->sigma_bar) : 0.0f;
+    a.maj.data = maj_len ? s_maj.dev : nullptr; a.maj.levels = P->majorant_levels;
+    a.maj.x0 = P->majorant_x0; a.maj.y0 = P->majorant_y0; a.maj.dx = P->majorant_dx; a.maj.dy = P->majorant_dy;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;
@@ -1369,7 +1388,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (s_steps.dev) CU(cudaMemcpyAsync(s_steps.dev, ctrs + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     bool sync = s_mean.host_out() || s_m2.host_out() || s_blk.host_out() || s_steps.host_out() || s_trace.host_out() || s_tlen.host_out();
     if (out_walk_vals && vals_temp) sync = true;
-    if ((rc = s_pts.finish()) || (rc = s_icdf.finish()) || (rc = s_mean.finish()) || (rc = s_m2.finish()) || (rc = s_blk.finish()) ||
+    if ((rc = s_pts.finish()) || (rc = s_icdf.finish()) || (rc = s_maj.finish()) || (rc = s_mean.finish()) || (rc = s_m2.finish()) || (rc = s_blk.finish()) ||
         (rc = s_steps.finish()) || (rc = s_trace.finish()) || (rc = s_tlen.finish())) return rc;
     if (vals_temp) CU(cudaFreeAsync(vals, st));
     if (d_srcs) CU(cudaFreeAsync(d_srcs, st));

@@ -299,6 +299,24 @@ def phys_varcoef_neumann_top() -> Scenario:
                     eps=1e-4, compat="physical", analytic=lambda p: (1.0 + p[:, 0]) * torch.cos(math.pi * (1.0 - p[:, 1])))
 
 
+def phys_dcr_halfspace(n_electrodes: int = 9) -> Scenario:
+    """DC resistivity the way the physics has it: half-space x in [-100, 100], y in [-100, 0] with an insulating surface
+    y = 0 (zero Neumann) and u = 0 on the far boundaries; conductivity 1 S/m with a smooth conductive body
+    (+4 S/m, Gaussian, 6 m wide) 25 m below the surface -- deep enough that d(alpha)/dy = 0 at the surface; a current
+    dipole (Gaussian electrodes, 2 m wide, 2 m deep) at x = -20 / +20; potential electrodes 1 m below the surface.
+    No analytic solution: checked against a finite-difference solve (tests/fd_reference.py)."""
+    d = torch.tensor([[-100.0, 0.0], [-100.0, -100.0], [100.0, -100.0], [100.0, 0.0]])      # left, bottom, right
+    n = torch.tensor([[100.0, 0.0], [-100.0, 0.0]])                                         # the surface
+    xs = torch.linspace(-40.0, 40.0, n_electrodes)
+    pts = torch.stack([xs, torch.full_like(xs, -1.0)], dim=1).contiguous()
+    w, amp = 2.0, 1.0 / (2.0 * math.pi * 2.0 ** 2)
+    q = 1.0 / (2.0 * w * w)
+    f = TermField.gaussian_sum([(amp, (-20.0, -2.0), q), (-amp, (20.0, -2.0), q)])
+    alpha = TermField.gaussian_sum([(4.0, (10.0, -25.0), 1.0 / (2.0 * 6.0 ** 2))], base=1.0)
+    return Scenario(name="phys_dcr_halfspace", dirichlet=d, neumann=n, points=pts, g=None, f=f, alpha=alpha, sigma=None,
+                    n_walks=20000, max_steps=20000, eps=1e-2, compat="physical")
+
+
 PHYSICAL_VARCOEF = {"phys_varcoef_dirichlet": phys_varcoef_dirichlet, "phys_varcoef_neumann": phys_varcoef_neumann_top}
 PHYSICAL = {"phys_laplace": phys_laplace_neumann_top, "phys_poisson": phys_poisson_neumann_top, "phys_cylinder": phys_cylinder}
 ALL = {"cfg1a": cfg1a, "cfg1b": cfg1b, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}

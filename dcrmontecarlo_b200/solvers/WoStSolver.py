@@ -51,7 +51,8 @@ class WostSolver_2D:
     def __init__(self, dirichletBoundary: PolyLines, dirichletBoundaryFunction: callable = None,
                  neumannBoundary: PolyLines = None, source: callable = None, sigma: callable = None,
                  alpha: callable = None, *, field_resolution: int = 257, sigma_prime_resolution: int = 65,
-                 sigma_prime_mode: str = "auto", compat: str = "reference", field_tolerance: float | None = 1e-3):
+                 sigma_prime_mode: str = "auto", compat: str = "reference", field_tolerance: float | None = 1e-3,
+                 majorant_resolution: int = 256):
         """``sigma_prime_mode``: ``"auto"`` differentiates the coefficients like the reference and falls back to
         ``sigma/alpha`` when that fails; ``"ratio"`` forces the fallback — what the reference ends up with for
         callables that wrap their result in ``torch.tensor(...)`` (tests/testWostVariableCoefficients.py:49,57,
@@ -67,6 +68,12 @@ class WostSolver_2D:
         if compat not in nat.COMPAT:
             raise ValueError("compat must be 'reference' or 'physical'")
         self.compat = compat
+        # physical mode with variable coefficients: cells per side of the spatially varying majorant (a power of two;
+        # 0 = one majorant for the whole domain)
+        self.majorant_resolution = int(majorant_resolution)
+        if self.majorant_resolution and (self.majorant_resolution & (self.majorant_resolution - 1) or self.majorant_resolution > 4096):
+            raise ValueError("majorant_resolution must be 0 or a power of two <= 4096")
+        self.majorant = None
         self.field_tolerance = field_tolerance       # callables that must be tabulated: refine the table to this relative error
         if sigma_prime_mode not in ("auto", "ratio", "full"):
             raise ValueError("sigma_prime_mode must be 'auto', 'ratio' or 'full'")
@@ -175,6 +182,9 @@ class WostSolver_2D:
         import warnings
 
         hosts = [(self._host_field(c) if given else None) for c, given in ((self.alpha, self._alpha_given), (self.sigma, self._sigma_given))]
+        N = self.majorant_resolution
+        if N and all(h is None or isinstance(h, TermField) for h in hosts):
+            n = 2 * N + 1                                                 # two lattice intervals per majorant cell
         if all(h is None or isinstance(h, TermField) for h in hosts):
             if self.sigma_prime_mode != "ratio":
                 self.sp_mode = SP_FULL if self._alpha_given else SP_RATIO    # closed form on the device, whatever autograd said
@@ -190,10 +200,28 @@ class WostSolver_2D:
                               "(exact only where alpha is constant)", RuntimeWarning)
             lo, hi, _, _ = gridSampleMinMax(self.sigma_prime, self.domain_bounds, grid_resolution=min(n, 65))
             vals = torch.tensor([lo, hi])
+        if N and vals.numel() == (2 * N + 1) ** 2:
+            self.majorant = self._majorant_pyramid(vals.reshape(2 * N + 1, 2 * N + 1), N)
         vals = vals[torch.isfinite(vals)]
         if vals.numel() == 0:
             raise ValueError("sigma' could not be evaluated anywhere on the domain lattice")
         return 1.05 * float(vals.abs().max())
+
+    def _majorant_pyramid(self, lattice: torch.Tensor, N: int) -> dict:
+        """Max-pyramid of |sigma'| (include/wost.h, ``wost_solve_params_t.majorant``): cell (i, j) of level 0 takes
+        1.05 x the largest |sigma'| on its 3 x 3 lattice nodes (corners, edge midpoints, centre); each further level the
+        maxima of 2 x 2 blocks.  Delta tracking stays unbiased if a cell value misses a narrow peak between nodes --
+        the weights 1 - sigma'/sigma_bar just leave [0, 1] there."""
+        import torch.nn.functional as Fn
+
+        a = torch.nan_to_num(lattice.abs().double(), nan=0.0, posinf=0.0)
+        cells = Fn.max_pool2d(a[None, None], kernel_size=3, stride=2)[0, 0] * 1.05          # (N, N), i along x
+        levels = [cells]
+        while levels[-1].shape[0] > 1:
+            levels.append(Fn.max_pool2d(levels[-1][None, None], kernel_size=2)[0, 0])
+        (x0, x1), (y0, y1) = self._bounds()
+        data = np.concatenate([l.numpy().astype(np.float32).ravel() for l in levels])
+        return dict(data=data, levels=len(levels), x0=x0, y0=y0, dx=(x1 - x0) / N, dy=(y1 - y0) / N)
 
     def _sigma_prime_lattice_vectorised(self, n):
         (x0, x1), (y0, y1) = [[float(a), float(b)] for a, b in self.domain_bounds]
@@ -282,6 +310,14 @@ class WostSolver_2D:
         keep = (g, f, alpha, sigma, sp)
         return self._scene(device), fields, icdf, keep
 
+    def _device_majorant(self, device):
+        if self.majorant is None or not self.use_delta_tracking or self.compat != "physical":
+            return None
+        key = ("majorant", device)
+        if key not in self._cache:
+            self._cache[key] = dict(self.majorant, data=torch.from_numpy(self.majorant["data"]).to(torch.device("cuda", device)))
+        return self._cache[key]
+
     def _sigma_prime_plain(self, point):
         """sigma' as a plain float callable, for tabulation when the coefficients are not analytic fields."""
         return float(self.sigma_prime(point))
@@ -305,7 +341,7 @@ class WostSolver_2D:
                         sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
                         point_index_base=point_index_base, walk_offset=walk_offset, want_block_stats=want_block_stats,
                         want_walk_vals=want_walk_vals, n_trace=n_trace, trace_cap=trace_cap, device_outputs=device_outputs,
-                        compat=self.compat)
+                        compat=self.compat, majorant=self._device_majorant(device))
         res["seed"] = seed
         return res
 
@@ -324,7 +360,8 @@ class WostSolver_2D:
         res = nat.solve_multi_source(scene, fields, devs, solvePoints, int(nWalks), int(maxSteps), float(eps),
                                      delta=self.use_delta_tracking, sp_mode=self.sp_mode,
                                      sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
-                                     want_block_stats=want_block_stats, device_outputs=device_outputs, compat=self.compat)
+                                     want_block_stats=want_block_stats, device_outputs=device_outputs, compat=self.compat,
+                                     majorant=self._device_majorant(device))
         res["seed"] = seed
         return res
 

@@ -51,7 +51,10 @@ def geometric_factor_2d(a, b, m, n) -> float:
 class DCRSurvey:
     def __init__(self, dirichletBoundary: PolyLines, neumannBoundary: PolyLines, conductivity: Field,
                  electrodes: torch.Tensor, sources: Sequence[DipoleSource], receivers: Sequence[tuple] | None = None,
-                 sink_sign: float = -1.0):
+                 sink_sign: float = -1.0, compat: str = "reference", **solver_kw):
+        """``compat="physical"`` runs the survey with the textbook estimator (reflections that do not leak, delta
+        tracking with a spatially varying majorant) instead of the reference's; further keyword arguments go to
+        ``WostSolver_2D``."""
         self.electrodes = torch.as_tensor(electrodes, dtype=torch.float32).reshape(-1, 2).contiguous()
         self.sources = list(sources)
         E = self.electrodes.shape[0]
@@ -59,7 +62,8 @@ class DCRSurvey:
         self.receivers = [(i, i + 1) for i in range(E - 1)] if receivers is None else [tuple(r) for r in receivers]
         self.sink_sign = float(sink_sign)
         # one solver: sigma' and sigma_bar depend on the conductivity only (no absorption in DC resistivity)
-        self.solver = WostSolver_2D(dirichletBoundary, None, neumannBoundary, source=None, sigma=None, alpha=conductivity)
+        self.solver = WostSolver_2D(dirichletBoundary, None, neumannBoundary, source=None, sigma=None, alpha=conductivity,
+                                    compat=compat, **solver_kw)
         self._fields = [s.field(self.sink_sign) for s in self.sources]
         self._streams: list = []
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WOST_VERSION 100   /* major*10000 + minor*100 + patch */
+#define WOST_VERSION 101   /* major*10000 + minor*100 + patch */
 
 typedef enum {
     WOST_OK = 0,
@@ -116,7 +116,15 @@ typedef struct {
     int64_t point_index_base; /* global index of pts[0]  } Philox counter = (point, walk, step, 0) */
     int64_t walk_offset;      /* global index of walk 0  }  => results independent of sharding     */
     int32_t compat_mode;      /* WOST_COMPAT_*                                                     */
-    int32_t reserved[3];
+    /* physical mode with variable coefficients: optional spatially varying majorant.  A max-pyramid of
+     * |sigma'| over the bounding box: level 0 has n x n cells (n = 2^(levels-1), cell (i,j) covers
+     * [x0+i dx, x0+(i+1) dx) x [y0+j dy, ...), value at [i*n+j]); level l+1 holds the maxima of 2x2 blocks of
+     * level l and follows it in memory; the last level is one cell.  Each step then uses the maximum over the cells
+     * its ball touches instead of sigma_bar, and steps are only capped where sigma' is large.  levels = 0: one
+     * majorant (sigma_bar) for the whole domain.  HOST or DEVICE pointer. */
+    int32_t majorant_levels;
+    const float* majorant;
+    float majorant_x0, majorant_y0, majorant_dx, majorant_dy;
 } wost_solve_params_t;
 
 #define WOST_WALK_BLOCK 1024   /* walks per deterministic reduction block */

@@ -697,6 +697,33 @@ double orc_phys_wall_weight(double t, double r, double sb) {
     return ct * (orc_k1(ct) * orc_i0(c) + orc_k0(c) * orc_i1(ct));
 }
 
+/* spatially varying majorant: maximum of the pyramid over the cells the ball touches, at the level whose cells are
+ * at least 2r wide */
+float orc_majorant_over_ball(const orc_params_t* p, float x, float y, float r) {
+    int l = 0, n = 1 << (p->maj_levels - 1), off = 0;
+    float cx = p->maj_dx, cy = p->maj_dy;
+    while ((cx < 2.0f * r || cy < 2.0f * r) && l < p->maj_levels - 1) { off += n * n; n >>= 1; cx *= 2.0f; cy *= 2.0f; ++l; }
+    int i0 = (int)floorf((x - r - p->maj_x0) / cx), i1 = (int)floorf((x + r - p->maj_x0) / cx);
+    int j0 = (int)floorf((y - r - p->maj_y0) / cy), j1 = (int)floorf((y + r - p->maj_y0) / cy);
+    i0 = i0 < 0 ? 0 : (i0 > n - 1 ? n - 1 : i0); i1 = i1 < 0 ? 0 : (i1 > n - 1 ? n - 1 : i1);
+    j0 = j0 < 0 ? 0 : (j0 > n - 1 ? n - 1 : j0); j1 = j1 < 0 ? 0 : (j1 > n - 1 ? n - 1 : j1);
+    const float* L = p->majorant + off;
+    float m = -1.0f;
+    for (int i = i0; i <= i1; ++i) for (int j = j0; j <= j1; ++j) { float v = L[i * n + j]; if (v > m) m = v; }
+    return m;
+}
+/* the largest r <= r0 (by halving, never below rmin) with r^2 M(ball(x, r)) <= 1 */
+float orc_majorant_radius(const orc_params_t* p, float x, float y, float r0, float rmin, float* M) {
+    float r = r0 > rmin ? r0 : rmin;
+    for (int it = 0; it < 48; ++it) {
+        *M = orc_majorant_over_ball(p, x, y, r);
+        if (r * r * *M <= 1.0f || r <= rmin) break;
+        float lo = 1.0f / sqrtf(*M), half = 0.5f * r;
+        r = half > lo ? half : lo; r = r > rmin ? r : rmin;
+    }
+    return r;
+}
+
 static float run_walk_physical_delta(const orc_params_t* p, walk_rng_t* g, float x0, float y0, uint32_t pidx, uint32_t widx,
                                      int32_t* n_steps, int32_t trace_cap, float* trace, int32_t* trace_len) {
     const int has_neu = p->neu_pts && p->n_neu > 0, has_src = p->f != NULL;
@@ -709,8 +736,12 @@ static float run_walk_physical_delta(const orc_params_t* p, walk_rng_t* g, float
         dD = phys_distance(p->dir_pts, p->n_dir, x, y, &cx, &cy);
         if (!(steps < p->max_steps && dD > eps && w != 0.0f)) break;
         float dN = has_neu ? phys_silhouette_distance(p->neu_pts, p->n_neu, x, y) : INFINITY;
-        float m = dN < dD ? dN : dD; m = m < rcap ? m : rcap;
-        float r = m > rmin ? m : rmin;
+        float m = dN < dD ? dN : dD, r, sbf = p->sigma_bar;
+        if (p->maj_levels > 0) {
+            float M; r = orc_majorant_radius(p, x, y, m, rmin, &M);
+            float floor_ = 1e-8f / (r * r); sbf = M > floor_ ? M : floor_;
+        } else { m = m < rcap ? m : rcap; r = m > rmin ? m : rmin; }
+        const double sb = (double)sbf;
         if (trace && steps < trace_cap) { float* t = trace + 4 * steps; t[0] = x; t[1] = y; t[2] = dD; t[3] = dN; }
         orc_philox4x32_10(pidx, widx, (uint32_t)steps, 2u, g->k0, g->k1, g->o);
         orc_philox4x32_10(pidx, widx, (uint32_t)steps, 3u, g->k0, g->k1, o2);
@@ -722,14 +753,14 @@ static float run_walk_physical_delta(const orc_params_t* p, walk_rng_t* g, float
         float th; int vis = 1;
         if (has_neu) vis = phys_ray(p->neu_pts, p->n_neu, x, y, sx_, sy_, rho, &th) < 0;
         const float yx = x + rho * sx_, yy = y + rho * sy_;
-        const float ratio = (float)orc_phys_green_ratio((double)rho, (double)r, (double)p->sigma_bar);
+        const float ratio = (float)orc_phys_green_ratio((double)rho, (double)r, sb);
         if (has_src && vis) total += w * (orc_field_eval(p->f, yx, yy) * (ratio * (r * r / 4.0f)) / sqrtf(alpha_at(p, yx, yy)));
-        const double c = (double)r * sqrt((double)p->sigma_bar), i0c = orc_i0(c), pv = i0_minus_1(c) / i0c;
+        const double c = (double)r * sqrt(sb), i0c = orc_i0(c), pv = i0_minus_1(c) / i0c;
         if ((double)u24(o2[0]) < pv) {                                       /* null-collision inside the star */
             if (!vis) w = 0.0f;
             else {
                 const float sp = orc_sigma_prime(p, yx, yy);
-                w = (w * (ratio * (float)(0.25 * c * c / pv))) * (1.0f - sp / p->sigma_bar);
+                w = (w * (ratio * (float)(0.25 * c * c / pv))) * (1.0f - sp / sbf);
                 x = yx; y = yy; onB = 0;
             }
         } else {
@@ -738,7 +769,7 @@ static float run_walk_physical_delta(const orc_params_t* p, walk_rng_t* g, float
                 float ux = p->neu_pts[2 * k + 2] - p->neu_pts[2 * k], uy = p->neu_pts[2 * k + 3] - p->neu_pts[2 * k + 1];
                 float len = norm2f(ux, uy), nx = -uy / len, ny = ux / len;
                 if (nx * ex + ny * ey > 0.0f) { nx = -nx; ny = -ny; }
-                w = w * (float)orc_phys_wall_weight((double)t_hit, (double)r, (double)p->sigma_bar);
+                w = w * (float)orc_phys_wall_weight((double)t_hit, (double)r, sb);
                 x = (x + t_hit * ex) + p->phys_nudge * nx; y = (y + t_hit * ey) + p->phys_nudge * ny;
                 phi_in = atan2f(ny, nx); onB = 1;
             } else { x = x + r * ex; y = y + r * ey; onB = 0; }

@@ -49,7 +49,9 @@ class _Params(C.Structure):
                 ("rng_mode", C.c_int32), ("seed", C.c_uint64), ("seed_numpy", C.c_uint64),
                 ("point_index_base", C.c_int64), ("walk_offset", C.c_int64),
                 ("icdf", C.c_void_p), ("icdf_len", C.c_int32), ("n_threads", C.c_int32),
-                ("sincos_fn", C.c_void_p), ("atan2_fn", C.c_void_p), ("compat_mode", C.c_int32), ("phys_nudge", C.c_float)]
+                ("sincos_fn", C.c_void_p), ("atan2_fn", C.c_void_p), ("compat_mode", C.c_int32), ("phys_nudge", C.c_float),
+                ("maj_levels", C.c_int32), ("majorant", C.c_void_p), ("maj_x0", C.c_float), ("maj_y0", C.c_float),
+                ("maj_dx", C.c_float), ("maj_dy", C.c_float)]
 
 
 SINCOS_FN = C.CFUNCTYPE(None, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float))
@@ -258,7 +260,8 @@ class Problem:
     """Scene + fields + walk parameters, packed for ``orc_solve``."""
 
     def __init__(self, dirichlet, neumann=None, g=None, f=None, alpha=None, sigma=None, sigma_prime=None,
-                 sigma_bar=0.0, sp_mode=SP_FULL, delta=None):
+                 sigma_bar=0.0, sp_mode=SP_FULL, delta=None, majorant=None):
+        self.majorant = majorant          # physical mode: dict(data, levels, x0, y0, dx, dy), see include/wost.h
         self.dir = _f32(dirichlet)
         self.neu = None if neumann is None else _f32(neumann)
         self.fields = {k: pack_field(v) for k, v in dict(g=g, f=f, alpha=alpha, sigma=sigma, sigma_prime=sigma_prime).items()}
@@ -268,10 +271,11 @@ class Problem:
         self._icdf = None
 
     @classmethod
-    def from_scenario(cls, s, sigma_bar=None):
+    def from_scenario(cls, s, sigma_bar=None, majorant=None):
         """(pass ``compat=s.compat`` to :meth:`solve` for the physical-mode scenes)"""
         sb = sigma_bar if sigma_bar is not None else (s.sigma_bar or 0.0)
-        return cls(s.dirichlet, s.neumann, g=s.g, f=s.f, alpha=s.alpha, sigma=s.sigma, sigma_bar=sb, sp_mode=s.sp_mode)
+        return cls(s.dirichlet, s.neumann, g=s.g, f=s.f, alpha=s.alpha, sigma=s.sigma, sigma_bar=sb, sp_mode=s.sp_mode,
+                   majorant=majorant)
 
     def params(self, n_walks, max_steps, eps, rng_mode, seed, seed_numpy=0, point_index_base=0, walk_offset=0,
                icdf=None, n_threads=0, torch_trig=False, compat="reference"):
@@ -294,6 +298,11 @@ class Problem:
             p.icdf, p.icdf_len = self._icdf_live.ctypes.data, len(self._icdf_live)
         p.n_threads = int(n_threads)
         p.compat_mode = {"reference": 0, "physical": 1}[compat]
+        if self.majorant is not None and compat == "physical":
+            m = self.majorant
+            self._maj_live = _f32(m["data"])
+            p.majorant, p.maj_levels = self._maj_live.ctypes.data, int(m["levels"])
+            p.maj_x0, p.maj_y0, p.maj_dx, p.maj_dy = float(m["x0"]), float(m["y0"]), float(m["dx"]), float(m["dy"])
         scale = float(np.abs(self.dir).max()) if self.neu is None else float(max(np.abs(self.dir).max(), np.abs(self.neu).max()))
         p.phys_nudge = np.float32(1e-5 * scale)
         if torch_trig:

@@ -532,19 +532,21 @@ def test_physical_mode_kernel_matches_oracle_and_analytic(key):
     assert torch.sqrt(((est[:, 0].double() - exact) ** 2).mean()) < 5e-3
 
 
+@pytest.mark.parametrize("res", [0, 256])
 @pytest.mark.parametrize("key", sorted(sc.PHYSICAL_VARCOEF))
-def test_physical_mode_variable_coefficients_match_oracle_and_analytic(key):
+def test_physical_mode_variable_coefficients_match_oracle_and_analytic(key, res):
     """compat="physical" with alpha(x), sigma(x): delta tracking with the screened kernel's own weights.  The oracle states
     the estimator in double-precision Bessel quadratures, the kernel in fp32 power series; both must agree walk by walk
     (to rounding, while the branch decisions coincide) and converge to the analytic solution — which the reference's
     estimator does not (cfg 1b plateaus at RMSE 0.028)."""
     s = sc.PHYSICAL_VARCOEF[key]()
-    solver = s.make_solver()
+    solver = s.make_solver(majorant_resolution=res)                      # one majorant / the max-pyramid of |sigma'|
     assert solver.compat == "physical" and solver.use_delta_tracking and solver.sp_mode == sc.SP_FULL
+    assert (solver.majorant is None) == (res == 0)
     W = 256
     r = solver.solve_raw(s.points, W, s.max_steps, s.eps, seed=77, want_walk_vals=True, n_trace=len(s.points) * W, trace_cap=6)
-    o = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar).solve(s.points, W, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=77,
-                                                                      compat="physical", walk_vals=True, n_trace=len(s.points) * W, trace_cap=6)
+    o = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar, majorant=solver.majorant).solve(
+        s.points, W, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=77, compat="physical", walk_vals=True, n_trace=len(s.points) * W, trace_cap=6)
     n3 = np.minimum(np.minimum(r["trace_len"], o["trace_len"]), 3)
     for i in range(len(n3)):
         assert np.allclose(r["trace"][i, : n3[i], :4], o["trace"][i, : n3[i]], rtol=1e-5, atol=2e-5), (key, i)
@@ -561,6 +563,36 @@ def test_physical_mode_variable_coefficients_match_oracle_and_analytic(key):
     m = solver.solve_multi_source(s.points, [s.f, s.f * 2.0], 300, s.max_steps, s.eps, seed=9)
     one = solver.solve_raw(s.points, 300, s.max_steps, s.eps, seed=9)
     assert np.array_equal(m["mean"][0], one["mean"]) and np.array_equal(m["m2"][0], one["m2"])
+
+
+def test_physical_dcr_halfspace_matches_oracle_and_finite_differences():
+    """DC resistivity as the physics has it (insulating surface, smooth conductive body, current dipole): kernel against the
+    oracle walk by walk, and against a finite-difference solve of the same boundary value problem."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import fd_reference as fd
+
+    s = sc.phys_dcr_halfspace()
+    solver = s.make_solver()
+    W = 128
+    r = solver.solve_raw(s.points, W, s.max_steps, s.eps, seed=4, want_walk_vals=True, n_trace=len(s.points) * W, trace_cap=4)
+    o = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar, majorant=solver.majorant).solve(
+        s.points, W, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=4, compat="physical", walk_vals=True, n_trace=len(s.points) * W, trace_cap=4)
+    n3 = np.minimum(np.minimum(r["trace_len"], o["trace_len"]), 3)
+    for i in range(len(n3)):
+        assert np.allclose(r["trace"][i, : n3[i], :4], o["trace"][i, : n3[i]], rtol=1e-5, atol=2e-4), i
+    assert abs(int(r["steps"][0]) - o["steps"]) <= 0.1 * o["steps"]
+    xs, ys, U = fd.solve_rectangle(-100, 100, -100, 0, 0.5, s.alpha, s.f)
+    ref = fd.interpolate(xs, ys, U, s.points.numpy())
+    est, stats = solver.solve(s.points, nWalks=1_000_000, maxSteps=s.max_steps, eps=s.eps, seed=8, return_stats=True)
+    z = (est[:, 0].double().numpy() - ref) / (stats["stderr"].numpy() + 0.01 * np.abs(ref).max())
+    assert np.all(np.abs(z) <= 3.5), z
+    # the local majorant only shortens steps near the body: fewer steps per walk than with one majorant for the domain
+    glob = s.make_solver(majorant_resolution=0)
+    a = solver.solve_raw(s.points, 4096, s.max_steps, s.eps, seed=1)["steps"][0]
+    b = glob.solve_raw(s.points, 4096, s.max_steps, s.eps, seed=1)["steps"][0]
+    assert a < 0.9 * b
 
 
 def test_physical_mode_dirichlet_only_and_unsupported_combinations():

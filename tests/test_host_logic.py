@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = nat.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.wost_version() == 100
+    assert L.wost_version() == 101
     assert L.wost_device_count() >= 0
 
 
@@ -37,7 +37,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(nat._Term) == 64
     assert C.sizeof(nat.FieldDesc) == 80                                    # 60 bytes of scalars, padded to 64, two pointers
     assert C.sizeof(nat.Fields) == 40
-    assert C.sizeof(nat.SolveParams) == 88
+    assert C.sizeof(nat.SolveParams) == 104
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the behaviour WITHOUT a GPU")

@@ -240,15 +240,18 @@ def test_physical_delta_weights_against_scipy():
     assert abs(m - (1 - 1 / sp.i0(c)) / (c * c / 4)) < 2e-3
 
 
+@pytest.mark.parametrize("local", [False, True])
 @pytest.mark.parametrize("key", sorted(sc.PHYSICAL_VARCOEF))
-def test_physical_mode_with_variable_coefficients_converges_to_analytic(key):
-    """Delta tracking by the book converges where the reference's estimator has a bias floor (cfg 1b: RMSE 0.028)."""
+def test_physical_mode_with_variable_coefficients_converges_to_analytic(key, local):
+    """Delta tracking by the book converges where the reference's estimator has a bias floor (cfg 1b: RMSE 0.028) --
+    with one majorant for the domain and with the spatially varying one (max-pyramid of |sigma'|)."""
     s = sc.PHYSICAL_VARCOEF[key]()
     solver = s.make_solver()                                             # host setup only: sigma', the majorant
-    assert solver.use_delta_tracking and solver.sigma_bar > 0
+    assert solver.use_delta_tracking and solver.sigma_bar > 0 and solver.majorant["levels"] == 9
+    assert abs(solver.majorant["data"][-1] - solver.sigma_bar) < 1e-5 * solver.sigma_bar   # top of the pyramid = global majorant
     nw = 30000
-    r = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar).solve(s.points, nw, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX,
-                                                                      seed=11, compat="physical")
+    r = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar, majorant=solver.majorant if local else None).solve(
+        s.points, nw, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=11, compat="physical")
     exact = s.analytic(s.points).numpy()
     z = np.abs(r["mean"] - exact) / (r["stderr"] + 3e-4)
     assert np.all(z <= 3.6), z
@@ -257,3 +260,54 @@ def test_physical_mode_with_variable_coefficients_converges_to_analytic(key):
         ref = sc.cfg1b()
         rr = orc.Problem.from_scenario(ref).solve(ref.points, nw, ref.max_steps, ref.eps, rng_mode=orc.RNG_PHILOX, seed=11)
         assert np.sqrt(np.mean((rr["mean"] - exact) ** 2)) > 0.02        # the reference's bias floor
+
+
+def test_majorant_pyramid_bounds_sigma_prime_over_balls():
+    """The value read for a ball dominates |sigma'| at points inside the ball, and the step radius satisfies r^2 M <= 1."""
+    import ctypes as C
+
+    s = sc.phys_dcr_halfspace()
+    solver = s.make_solver()
+    prob = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar, majorant=solver.majorant)
+    p = prob.params(1, 1, 1e-2, orc.RNG_PHILOX, 0, compat="physical")
+    L = orc.lib()
+    L.orc_majorant_over_ball.restype = C.c_float
+    L.orc_majorant_over_ball.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+    L.orc_majorant_radius.restype = C.c_float
+    L.orc_majorant_radius.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]
+    L.orc_sigma_prime.restype = C.c_float
+    L.orc_sigma_prime.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        x, y = rng.uniform(-95, 95), rng.uniform(-95, -1)
+        r = float(10 ** rng.uniform(-2, 1.9))
+        M = L.orc_majorant_over_ball(C.byref(p), x, y, r)
+        th, rho = rng.uniform(0, 2 * np.pi, 40), r * np.sqrt(rng.random(40))
+        inside = [abs(L.orc_sigma_prime(C.byref(p), float(x + a * np.cos(t)), float(y + a * np.sin(t)))) for t, a in zip(th, rho)]
+        assert M >= max(inside) * 0.999, (x, y, r, M, max(inside))
+        Mr = C.c_float(0)
+        rr = L.orc_majorant_radius(C.byref(p), x, y, r, 5e-3, C.byref(Mr))
+        assert rr <= r * 1.000001 and (rr * rr * Mr.value <= 1.000001 or rr <= 5e-3)
+    # far from the body sigma' vanishes: the step is not capped there, while the global majorant would cap it at 6.5 m
+    Mr = C.c_float(0)
+    assert L.orc_majorant_radius(C.byref(p), -80.0, -10.0, 10.0, 5e-3, C.byref(Mr)) == 10.0
+    assert 1.0 / np.sqrt(solver.sigma_bar) < 7.0
+
+
+def test_physical_dcr_halfspace_matches_finite_differences():
+    """Half-space with a smooth conductive body, current dipole, insulating surface: no analytic solution, so the
+    estimator (oracle side) is compared with a finite-difference solve of the same boundary value problem."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import fd_reference as fd
+
+    s = sc.phys_dcr_halfspace()
+    xs, ys, U = fd.solve_rectangle(-100, 100, -100, 0, 1.0, s.alpha, s.f)
+    ref = fd.interpolate(xs, ys, U, s.points.numpy())
+    solver = s.make_solver()
+    r = orc.Problem.from_scenario(s, sigma_bar=solver.sigma_bar, majorant=solver.majorant).solve(
+        s.points, 6000, s.max_steps, s.eps, rng_mode=orc.RNG_PHILOX, seed=2, compat="physical")
+    z = np.abs(r["mean"] - ref) / (r["stderr"] + 0.01 * np.abs(ref).max())
+    assert np.all(z <= 3.5), z
+    assert 60 < r["steps"] / 6000 / len(s.points) < 200                 # ~110 steps per walk with the local majorant
