@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 if (edge) {
                     atten = atten * ratio;                                              // :277
                 } else {
-                    const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy);            // :281
+                    const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy, alpha_t);   // :281 (alpha(sample) is alpha_t here)
                     const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);              // :282
                     atten = (atten * ratio) * sc;                                       // :283
                 }
