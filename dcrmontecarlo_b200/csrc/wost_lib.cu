@@ -100,10 +100,29 @@ template <bool NEU, bool SRC, bool DELTA, bool TRACE, bool PHYS, bool BIG>
 __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
     extern __shared__ float4 smem[];
     const float4* dseg = a.dseg; const float4* nseg = a.nseg;
+    // Shared memory: [field headers: g, f, alpha, sigma, sigma', then the sources of a shared-walk solve][segment tables]
+    // [the fields' term tables].  The field interpreter reads headers and terms from here (wost_device.cuh, SM = true).
+    {
+        const int nf = FIELD_SOURCE0 + a.n_src;
+        uint32_t* hdr = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < nf * DEVFIELD_F4 * 4; i += blockDim.x) {
+            const int f = i / (DEVFIELD_F4 * 4), w = i - f * (DEVFIELD_F4 * 4);
+            const uint32_t* src = f < FIELD_SOURCE0 ? reinterpret_cast<const uint32_t*>(&a.F.g + f) : reinterpret_cast<const uint32_t*>(a.srcs + (f - FIELD_SOURCE0));
+            hdr[i] = src[w];
+        }
+        __syncthreads();
+        const DevField* sF = reinterpret_cast<const DevField*>(smem);
+        for (int f = 0; f < nf; ++f) {
+            const int n4 = 4 * sF[f].n_terms, off = sF[f].term_off;
+            const float4* src = reinterpret_cast<const float4*>(sF[f].terms);
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) smem[off + i] = __ldg(src + i);
+        }
+        __syncthreads();
+    }
     // segment tables without a hierarchy are staged into shared memory (all lanes read the same segment: broadcast);
     // polylines with a hierarchy are read through L1 by the traversals.  stage_smem: bit 0 Dirichlet, bit 1 Neumann.
     {
-        float4* sp = smem;
+        float4* sp = smem + DEVFIELD_F4 * (FIELD_SOURCE0 + a.n_src);
         if (a.stage_smem & 1) {
             for (int i = threadIdx.x; i < 2 * a.n_dseg; i += blockDim.x) sp[i] = a.dseg[i];
             dseg = sp; sp += 2 * a.n_dseg;
@@ -166,7 +185,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 x = __ldg(a.pts + 2 * p); y = __ldg(a.pts + 2 * p + 1);
                 dD = 1.0f;                                             // :190 sentinel (Q6)
                 atten = 1.0f; total_v = 0.0f; onB = false; phi_n = 0.0f; steps = 0;   // :188-195
-                if (DELTA) alpha_x = __ldg(a.alpha0 + p);                // = alpha_at(a.F, x, y), evaluated once per point
+                if (DELTA) alpha_x = __ldg(a.alpha0 + p);                // = alpha_at<true>(a.F, x, y), evaluated once per point
                 if (PHYS && DELTA) atten = 1.0f / sqrtf(alpha_x);          // u = U / sqrt(alpha): the walk estimates U
                 active = true;
             }
@@ -188,8 +207,8 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 const float gx_ = p0.x, gy_ = p0.y, w_ = p0.z, tot_ = p0.w;
                 const unsigned long long pid = ((unsigned long long)__float_as_uint(p1.y) << 32) | __float_as_uint(p1.x);
                 float bc = 0.0f;
-                if (a.F.g.present) bc = DELTA ? field_eval(a.F.g, gx_, gy_) : field_eval_inl(a.F.g, gx_, gy_);
-                if (PHYS && DELTA) bc = w_ * (bc * sqrtf(alpha_at(a.F, gx_, gy_)));   // U = sqrt(alpha) g on the boundary
+                if (a.F.g.present) bc = DELTA ? field_eval_s(FIELD_G, gx_, gy_) : field_eval_inl<true>(shared_field(FIELD_G), gx_, gy_);
+                if (PHYS && DELTA) bc = w_ * (bc * sqrtf(alpha_at<true>(a.F, gx_, gy_)));   // U = sqrt(alpha) g on the boundary
                 else if (DELTA) bc = bc * w_;
                 if (SRC && a.n_src > 0) {                                     // one total per source: same walk, same boundary term
                     float* row = a.walk_vals + (size_t)pid * a.n_src;
@@ -422,7 +441,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                     pd_k0c = sc - (0.5f * logf(pd_qc) + EULER_GAMMA) * pd_i0c;
                     pd_ratio = phys_green_ratio(pd_i0c, sc, pd_qc * u23, -0.5f * logf(u23));
                     pd_yx = yx; pd_yy = yy; pd_vis = vis;
-                    if (SRC && vis) wsrc = atten * ((pd_ratio * wsrc) / sqrtf(alpha_at(a.F, yx, yy)));
+                    if (SRC && vis) wsrc = atten * ((pd_ratio * wsrc) / sqrtf(alpha_at<true>(a.F, yx, yy)));
                 }
                 float pc = 0.0f;
                 if (SRC && a.n_src > 0) {
@@ -431,12 +450,12 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                         for (int k = 0; k < a.n_src; ++k) {
                             const float4 sup = __ldg(a.src_support + k);
                             if ((yx - sup.x) * (yx - sup.x) + (yy - sup.y) * (yy - sup.y) > sup.z) continue;   // exactly zero there
-                            const float ck = field_eval(a.srcs[k], yx, yy) * wsrc;
+                            const float ck = field_eval_s(FIELD_SOURCE0 + k, yx, yy) * wsrc;
                             if (ck != 0.0f) row[k] = row[k] + ck;
                         }
                     }
                 } else if (SRC) {
-                    pc = vis ? (DELTA ? field_eval(a.F.f, yx, yy) : field_eval_inl(a.F.f, yx, yy)) * wsrc : 0.0f;
+                    pc = vis ? (DELTA ? field_eval_s(FIELD_F, yx, yy) : field_eval_inl<true>(shared_field(FIELD_F), yx, yy)) * wsrc : 0.0f;
                     total_v += pc;
                 }
                 if (TRACE && SRC) {
@@ -486,7 +505,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
             if (PHYS && DELTA && pd_vol) {
                 if (!pd_vis) { atten = 0.0f; qx = x; qy = y; }                          // the sample fell behind a wall
                 else {
-                    const float sp = sigma_prime_at(a.F, a.sp_mode, pd_yx, pd_yy);
+                    const float sp = sigma_prime_at<true>(a.F, a.sp_mode, pd_yx, pd_yy);
                     atten = (atten * (pd_ratio * (pd_qc * pd_i0c / pd_m1))) * (1.0f - sp / pd_sb);
                     qx = pd_yx; qy = pd_yy;
                 }
@@ -521,19 +540,19 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                         // accumulates exactly the sum a single-source solve would (same expressions, same order)
                         float* row = a.walk_vals + (size_t)id * a.n_src;
                         float den = 1.0f;
-                        if (DELTA) { alpha_s = alpha_at(a.F, sx, sy); have_alpha_s = true; den = sqrtf(alpha_s * alpha_x); }
+                        if (DELTA) { alpha_s = alpha_at<true>(a.F, sx, sy); have_alpha_s = true; den = sqrtf(alpha_s * alpha_x); }
                         const float w4 = r * r / 4.0f;
                         for (int k = 0; k < a.n_src; ++k) {
                             const float4 sup = __ldg(a.src_support + k);
                             if ((sx - sup.x) * (sx - sup.x) + (sy - sup.y) * (sy - sup.y) > sup.z) continue;   // exactly zero there
-                            const float fk = field_eval(a.srcs[k], sx, sy);
+                            const float fk = field_eval_s(FIELD_SOURCE0 + k, sx, sy);
                             if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);   // fk != 0: plain division
                         }
                     } else if (DELTA) {                                                 // :252-254
-                        alpha_s = alpha_at(a.F, sx, sy); have_alpha_s = true;
-                        contrib = div_z(field_eval(a.F.f, sx, sy) * gn, sqrtf(alpha_s * alpha_x)) * atten;
+                        alpha_s = alpha_at<true>(a.F, sx, sy); have_alpha_s = true;
+                        contrib = div_z(field_eval_s(FIELD_F, sx, sy) * gn, sqrtf(alpha_s * alpha_x)) * atten;
                     } else
-                        contrib = field_eval_inl(a.F.f, sx, sy) * (r * r / 4.0f);       // :256
+                        contrib = field_eval_inl<true>(shared_field(FIELD_F), sx, sy) * (r * r / 4.0f);       // :256
                 }
                 if (SRC) total_v += contrib;                                            // :258
                 if (TRACE && SRC) {                                                     // :261-267 history: the source sample
@@ -547,12 +566,12 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 // branch at next_point, the interior branch at sample_point unless the source term already did).
                 const bool edge = u24(o[1]) > sbgn;
                 const float tx = edge ? qx : sx, ty = edge ? qy : sy;
-                const float alpha_t = (!edge && have_alpha_s) ? alpha_s : alpha_at(a.F, tx, ty);
+                const float alpha_t = (!edge && have_alpha_s) ? alpha_s : alpha_at<true>(a.F, tx, ty);
                 const float ratio = sqrtf(alpha_t / alpha_x);
                 if (edge) {
                     atten = atten * ratio;                                              // :277
                 } else {
-                    const float sp = sigma_prime_at(a.F, a.sp_mode, sx, sy, alpha_t);   // :281 (alpha(sample) is alpha_t here)
+                    const float sp = sigma_prime_at<true>(a.F, a.sp_mode, sx, sy, alpha_t);   // :281 (alpha(sample) is alpha_t here)
                     const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);              // :282
                     atten = (atten * ratio) * sc;                                       // :283
                 }
@@ -1282,10 +1301,23 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     float* vals = nullptr; bool vals_temp = false;
     const bool vals_dev_out = out_walk_vals && is_device_ptr(out_walk_vals);
     if (!vals_dev_out) { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)pts_per_pass * W * S, st)); vals_temp = true; }
+    // shared-memory layout of the walk kernel (float4 units): field headers | staged segment tables | term tables
+    const size_t d_bytes = scene->dbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_dseg;
+    const size_t n_bytes = scene->nbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_nseg;
+    const int stage_smem = (d_bytes + n_bytes <= 96 * 1024) ? ((d_bytes ? 1 : 0) | (n_bytes ? 2 : 0)) : 0;
+    DevFields DF = dev_fields_of(fields);
+    size_t smem_f4 = (size_t)DEVFIELD_F4 * (FIELD_SOURCE0 + n_sources) + (stage_smem ? (d_bytes + n_bytes) / sizeof(float4) : 0);
+    for (DevField* f : {&DF.g, &DF.f, &DF.alpha, &DF.sigma, &DF.sigma_prime}) { f->term_off = (int32_t)smem_f4; smem_f4 += 4 * (size_t)f->n_terms; }
     DevField* d_srcs = nullptr; float4* d_sup = nullptr;
+    std::vector<DevField> h(n_sources); std::vector<float4> hs(n_sources);
+    for (int k = 0; k < n_sources; ++k) {
+        h[k] = sources[k]->d; hs[k] = sources[k]->support;
+        h[k].term_off = (int32_t)smem_f4; smem_f4 += 4 * (size_t)h[k].n_terms;
+    }
+    const size_t smem = smem_f4 * sizeof(float4);
+    if (smem + 16 * 1024 > scene->smem_optin)
+        return fail(WOST_ERR_UNSUPPORTED, "field term tables and segment tables do not fit shared memory (" + std::to_string(smem) + " bytes)");
     if (n_sources > 0) {
-        std::vector<DevField> h(n_sources); std::vector<float4> hs(n_sources);
-        for (int k = 0; k < n_sources; ++k) { h[k] = sources[k]->d; hs[k] = sources[k]->support; }
         CU(cudaMallocAsync((void**)&d_srcs, sizeof(DevField) * n_sources, st));
         CU(cudaMallocAsync((void**)&d_sup, sizeof(float4) * n_sources, st));
         CU(cudaMemcpyAsync(d_srcs, h.data(), sizeof(DevField) * n_sources, cudaMemcpyHostToDevice, st));
@@ -1306,7 +1338,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
 
     WalkArgs a{};
     a.dseg = scene->dseg; a.n_dseg = scene->n_dseg; a.nseg = scene->nseg; a.n_nseg = scene->n_nseg;
-    a.F = dev_fields_of(fields);
+    a.F = DF;
     a.n_src = n_sources; a.srcs = d_srcs; a.src_support = d_sup;
     if (alpha0) { alpha0_kernel<<<blocks_for(n_pts, 256), 256, 0, st>>>(a.F, s_pts.dev, n_pts, alpha0); CU(cudaGetLastError()); }
     a.pts = s_pts.dev; a.n_pts = n_pts; a.n_walks = W;
@@ -1338,10 +1370,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
     const int threads = 256;
-    const size_t d_bytes = scene->dbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_dseg;
-    const size_t n_bytes = scene->nbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_nseg;
-    a.stage_smem = (d_bytes + n_bytes <= 96 * 1024) ? ((d_bytes ? 1 : 0) | (n_bytes ? 2 : 0)) : 0;
-    const size_t smem = a.stage_smem ? d_bytes + n_bytes : 0;
+    a.stage_smem = stage_smem;
     const bool phys = P->compat_mode == WOST_COMPAT_PHYSICAL;
     const bool big = scene->dbvh != nullptr || scene->nbvh != nullptr;
     walk_kernel_t kern = big ? (trace ? pick_kernel<true, true>(neu, src, delta, phys) : pick_kernel<false, true>(neu, src, delta, phys))
