@@ -101,8 +101,10 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
     extern __shared__ float4 smem[];
     const float4* dseg = a.dseg; const float4* nseg = a.nseg;
     // Shared memory: [field headers: g, f, alpha, sigma, sigma', then the sources of a shared-walk solve][segment tables]
-    // [the fields' term tables].  The field interpreter reads headers and terms from here (wost_device.cuh, SM = true).
-    {
+    // [the fields' term tables].  The delta-tracking kernels' out-of-line field interpreter reads headers and terms from
+    // here (wost_device.cuh, SM = true); the other kernels inline the interpreter and read the kernel parameters directly.
+    constexpr bool SMF = DELTA || (!NEU && !SRC);      // (measured: +24 % cfg 1b, +5 % cfg 1a, -2 % on the mixed-boundary Laplace kernel)
+    if (SMF) {
         const int nf = FIELD_SOURCE0 + a.n_src;
         uint32_t* hdr = reinterpret_cast<uint32_t*>(smem);
         for (int i = threadIdx.x; i < nf * DEVFIELD_F4 * 4; i += blockDim.x) {
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 const float gx_ = p0.x, gy_ = p0.y, w_ = p0.z, tot_ = p0.w;
                 const unsigned long long pid = ((unsigned long long)__float_as_uint(p1.y) << 32) | __float_as_uint(p1.x);
                 float bc = 0.0f;
-                if (a.F.g.present) bc = DELTA ? field_eval_s(FIELD_G, gx_, gy_) : field_eval_inl<true>(shared_field(FIELD_G), gx_, gy_);
+                if (a.F.g.present) bc = DELTA ? field_eval_s(FIELD_G, gx_, gy_) : (SMF ? field_eval_inl<true>(shared_field(FIELD_G), gx_, gy_) : field_eval_inl<false>(a.F.g, gx_, gy_));
                 if (PHYS && DELTA) bc = w_ * (bc * sqrtf(alpha_at<true>(a.F, gx_, gy_)));   // U = sqrt(alpha) g on the boundary
                 else if (DELTA) bc = bc * w_;
                 if (SRC && a.n_src > 0) {                                     // one total per source: same walk, same boundary term
@@ -450,12 +452,12 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                         for (int k = 0; k < a.n_src; ++k) {
                             const float4 sup = __ldg(a.src_support + k);
                             if ((yx - sup.x) * (yx - sup.x) + (yy - sup.y) * (yy - sup.y) > sup.z) continue;   // exactly zero there
-                            const float ck = field_eval_s(FIELD_SOURCE0 + k, yx, yy) * wsrc;
+                            const float ck = (SMF ? field_eval_s(FIELD_SOURCE0 + k, yx, yy) : field_eval(a.srcs[k], yx, yy)) * wsrc;
                             if (ck != 0.0f) row[k] = row[k] + ck;
                         }
                     }
                 } else if (SRC) {
-                    pc = vis ? (DELTA ? field_eval_s(FIELD_F, yx, yy) : field_eval_inl<true>(shared_field(FIELD_F), yx, yy)) * wsrc : 0.0f;
+                    pc = vis ? (DELTA ? field_eval_s(FIELD_F, yx, yy) : field_eval_inl<false>(a.F.f, yx, yy)) * wsrc : 0.0f;
                     total_v += pc;
                 }
                 if (TRACE && SRC) {
@@ -545,14 +547,14 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                         for (int k = 0; k < a.n_src; ++k) {
                             const float4 sup = __ldg(a.src_support + k);
                             if ((sx - sup.x) * (sx - sup.x) + (sy - sup.y) * (sy - sup.y) > sup.z) continue;   // exactly zero there
-                            const float fk = field_eval_s(FIELD_SOURCE0 + k, sx, sy);
+                            const float fk = SMF ? field_eval_s(FIELD_SOURCE0 + k, sx, sy) : field_eval(a.srcs[k], sx, sy);
                             if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);   // fk != 0: plain division
                         }
                     } else if (DELTA) {                                                 // :252-254
                         alpha_s = alpha_at<true>(a.F, sx, sy); have_alpha_s = true;
                         contrib = div_z(field_eval_s(FIELD_F, sx, sy) * gn, sqrtf(alpha_s * alpha_x)) * atten;
                     } else
-                        contrib = field_eval_inl<true>(shared_field(FIELD_F), sx, sy) * (r * r / 4.0f);       // :256
+                        contrib = field_eval_inl<false>(a.F.f, sx, sy) * (r * r / 4.0f);       // :256
                 }
                 if (SRC) total_v += contrib;                                            // :258
                 if (TRACE && SRC) {                                                     // :261-267 history: the source sample

@@ -11,7 +11,7 @@ import torch
 
 from dcrmontecarlo_b200 import _native as nat
 from dcrmontecarlo_b200 import scenarios as sc
-from dcrmontecarlo_b200.fields import GridField, TermField
+from dcrmontecarlo_b200.fields import GridField, TermField, make_term
 from dcrmontecarlo_b200.geometry.PolylinesSimple import PolyLinesSimple
 from dcrmontecarlo_b200.solvers.WoStSolver import WostSolver_2D
 from oracle import wost_oracle as orc
@@ -593,6 +593,23 @@ def test_physical_dcr_halfspace_matches_oracle_and_finite_differences():
     a = solver.solve_raw(s.points, 4096, s.max_steps, s.eps, seed=1)["steps"][0]
     b = glob.solve_raw(s.points, 4096, s.max_steps, s.eps, seed=1)["steps"][0]
     assert a < 0.9 * b
+
+
+def test_field_tables_in_shared_memory_limits_and_many_sources():
+    """The walk kernel keeps field headers and term tables in shared memory: many sources of a shared-walk solve still
+    fit (and reproduce single-source solves), an absurd term count is refused loudly instead of overflowing."""
+    s = sc.cfg3()
+    solver = s.make_solver()
+    pts = s.points[::40].contiguous()
+    srcs = [TermField.gaussian_sum([(1.0 + 0.01 * k, (-1.5 + 0.01 * k, 0.3), 3.0), (-0.5, (0.5, -1.0 + 0.005 * k), 5.0)]) for k in range(300)]
+    m = solver.solve_multi_source(pts, srcs, 256, s.max_steps, s.eps, seed=21)
+    for k in (0, 137, 299):
+        solver.setSourceTerm(srcs[k])
+        one = solver.solve_raw(pts, 256, s.max_steps, s.eps, seed=21)
+        assert np.array_equal(m["mean"][k], one["mean"]) and np.array_equal(m["m2"][k], one["m2"]), k
+    huge = TermField(0.0, [make_term(A=1e-3, px=k % 3, py=(k // 3) % 3) for k in range(4000)])
+    with pytest.raises(nat.WostError, match="shared memory"):
+        WostSolver_2D(PolyLinesSimple(s.dirichlet), s.g, None, huge).solve(pts, nWalks=8)
 
 
 def test_physical_mode_dirichlet_only_and_unsupported_combinations():
