@@ -32,8 +32,8 @@ POINTS = int(os.environ.get("WOST_BENCH_POINTS", 65536))
 WALKS = int(os.environ.get("WOST_BENCH_WALKS", 256))
 F_STEP_CFG2 = 1625.0          # algorithmic fp32 flops per walk step for S_D=4, V_N=33
 # dram__bytes_read.sum + dram__bytes_write.sum of one walk_kernel launch of this workload, from the committed
-# `ncu --set full` capture profiles/r1_v6_walk_kernel_ncu_full.csv (0.60 MB read + 12.30 MB written)
-DRAM_TRAFFIC_PER_LAUNCH = 12_900_352
+# `ncu --set full` capture profiles/r1_v7_walk_kernel_ncu_full.csv (0.60 MB read + 14.77 MB written)
+DRAM_TRAFFIC_PER_LAUNCH = 15_365_888
 METRIC, UNIT = "wost_walk_steps_per_sec", "walk-steps/s"
 
 
@@ -235,7 +235,7 @@ def main():
                        "parallelism": f"points sharded over {world} GPU(s), no data-path collective", "compat": "reference"},
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "traffic": DRAM_TRAFFIC_PER_LAUNCH if (POINTS, WALKS) == (65536, 256) else None,
-                         "traffic_note": "bytes per launch from profiles/r1_v6_walk_kernel_ncu_full.csv; algorithmic bytes per launch = "
+                         "traffic_note": "bytes per launch from profiles/r1_v7_walk_kernel_ncu_full.csv; algorithmic bytes per launch = "
                                          f"{POINTS * 8 + POINTS * WALKS * 4} (points in, per-walk totals out, mostly L2-resident)",
                          "flops_per_walk_step": F_STEP_CFG2,
                          "peak_source": "FMA-chain microbenchmark in this run (wost_fp32_peak); MEASURED_PEAKS.json has no fp32 entry",
