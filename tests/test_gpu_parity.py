@@ -595,6 +595,30 @@ def test_physical_dcr_halfspace_matches_oracle_and_finite_differences():
     assert a < 0.9 * b
 
 
+def test_physical_survey_matches_finite_differences():
+    """DCRSurvey(compat="physical"): shared walks for two current dipoles over the half-space with a conductive body;
+    potentials and receiver voltages against finite-difference solves."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import fd_reference as fd
+    from dcrmontecarlo_b200.survey import DCRSurvey, DipoleSource
+
+    s = sc.phys_dcr_halfspace()
+    dips = [DipoleSource((-20.0, -2.0), (20.0, -2.0), width=2.0), DipoleSource((-30.0, -2.0), (-10.0, -2.0), width=2.0)]
+    sv = DCRSurvey(PolyLinesSimple(s.dirichlet), PolyLinesSimple(s.neumann), s.alpha, s.points, dips, compat="physical")
+    assert sv.solver.compat == "physical" and sv.solver.majorant is not None
+    out = sv.run(nWalks=400_000, maxSteps=s.max_steps, eps=s.eps, seed=3, shared_walks=True)
+    for k, d in enumerate(dips):
+        xs, ys, U = fd.solve_rectangle(-100, 100, -100, 0, 1.0, s.alpha, d.field(-1.0))
+        ref = fd.interpolate(xs, ys, U, s.points.numpy())
+        z = (out["potentials"][k] - ref) / (out["stderr"][k] + 0.015 * np.abs(ref).max())
+        assert np.all(np.abs(z) <= 3.5), (k, z)
+        dv_ref = ref[:-1] - ref[1:]
+        assert np.all(np.abs(out["dV"][k] - dv_ref) <= 3.5 * out["dV_stderr"][k] + 0.03 * np.abs(dv_ref).max()), k
+    assert np.allclose(out["potentials"][0], s.make_solver().solve_raw(s.points, 400_000, s.max_steps, s.eps, seed=3)["mean"], rtol=0, atol=0)
+
+
 def test_field_tables_in_shared_memory_limits_and_many_sources():
     """The walk kernel keeps field headers and term tables in shared memory: many sources of a shared-walk solve still
     fit (and reproduce single-source solves), an absurd term count is refused loudly instead of overflowing."""
