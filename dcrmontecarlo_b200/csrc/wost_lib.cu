@@ -787,6 +787,21 @@ struct Staged {
         return 0;
     }
     bool host_out() const { return temp && is_out; }
+    ~Staged() { if (temp && dev) cudaFreeAsync(dev, st); }             // error paths: finish() was not reached
+    Staged() = default;
+    Staged(const Staged&) = delete;
+    Staged& operator=(const Staged&) = delete;
+};
+
+// stream-ordered scratch buffer, released on every exit path
+template <typename T>
+struct Scratch {
+    T* p = nullptr; cudaStream_t st = nullptr;
+    int alloc(size_t n, cudaStream_t s) { st = s; CU(cudaMallocAsync((void**)&p, n * sizeof(T), s)); return 0; }
+    ~Scratch() { if (p) cudaFreeAsync(p, st); }
+    Scratch() = default;
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
 };
 
 struct DeviceGuard {
@@ -1300,9 +1315,10 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (const char* e = std::getenv("WOST_MAX_WALK_VALS")) max_vals = std::max(1ll, std::atoll(e));
     if (W > max_vals) max_vals = W;                                     // at least one point per pass
     const long long pts_per_pass = std::max(1ll, std::min((long long)n_pts, max_vals / (W * S)));
+    Scratch<float> vals_s, alpha0_s; Scratch<DevField> srcs_s; Scratch<float4> sup_s; Scratch<unsigned long long> ctrs_s; Scratch<double> blk_s;
     float* vals = nullptr; bool vals_temp = false;
     const bool vals_dev_out = out_walk_vals && is_device_ptr(out_walk_vals);
-    if (!vals_dev_out) { CU(cudaMallocAsync((void**)&vals, sizeof(float) * (size_t)pts_per_pass * W * S, st)); vals_temp = true; }
+    if (!vals_dev_out) { if ((rc = vals_s.alloc((size_t)pts_per_pass * W * S, st))) return rc; vals = vals_s.p; vals_temp = true; }
     // shared-memory layout of the walk kernel (float4 units): field headers | staged segment tables | term tables
     const size_t d_bytes = scene->dbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_dseg;
     const size_t n_bytes = scene->nbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_nseg;
@@ -1320,19 +1336,19 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (smem + 16 * 1024 > scene->smem_optin)
         return fail(WOST_ERR_UNSUPPORTED, "field term tables and segment tables do not fit shared memory (" + std::to_string(smem) + " bytes)");
     if (n_sources > 0) {
-        CU(cudaMallocAsync((void**)&d_srcs, sizeof(DevField) * n_sources, st));
-        CU(cudaMallocAsync((void**)&d_sup, sizeof(float4) * n_sources, st));
+        if ((rc = srcs_s.alloc(n_sources, st)) || (rc = sup_s.alloc(n_sources, st))) return rc;
+        d_srcs = srcs_s.p; d_sup = sup_s.p;
         CU(cudaMemcpyAsync(d_srcs, h.data(), sizeof(DevField) * n_sources, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_sup, hs.data(), sizeof(float4) * n_sources, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));                                   // the host vectors go out of scope
     }
-    unsigned long long* ctrs = nullptr;
-    CU(cudaMallocAsync((void**)&ctrs, 2 * sizeof(unsigned long long), st));
-    float* alpha0 = nullptr;
-    if (delta) CU(cudaMallocAsync((void**)&alpha0, sizeof(float) * (size_t)n_pts, st));
+    if ((rc = ctrs_s.alloc(2, st))) return rc;
+    unsigned long long* ctrs = ctrs_s.p;
+    if (delta && (rc = alpha0_s.alloc((size_t)n_pts, st))) return rc;
+    float* alpha0 = alpha0_s.p;
     CU(cudaMemsetAsync(ctrs, 0, 2 * sizeof(unsigned long long), st));
     double* blk = s_blk.dev; bool blk_temp = false;
-    if (!blk) { CU(cudaMallocAsync((void**)&blk, sizeof(double) * 2 * n_pts * nblk * S, st)); blk_temp = true; }
+    if (!blk) { if ((rc = blk_s.alloc((size_t)2 * n_pts * nblk * S, st))) return rc; blk = blk_s.p; blk_temp = true; }
     if (trace) {
         CU(cudaMemsetAsync(s_trace.dev, 0xff, sizeof(float) * (size_t)n_trace * (trace_cap + 1) * 8, st));   // NaN fill
         CU(cudaMemsetAsync(s_tlen.dev, 0, sizeof(int32_t) * n_trace, st));
@@ -1421,12 +1437,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (out_walk_vals && vals_temp) sync = true;
     if ((rc = s_pts.finish()) || (rc = s_icdf.finish()) || (rc = s_maj.finish()) || (rc = s_mean.finish()) || (rc = s_m2.finish()) || (rc = s_blk.finish()) ||
         (rc = s_steps.finish()) || (rc = s_trace.finish()) || (rc = s_tlen.finish())) return rc;
-    if (vals_temp) CU(cudaFreeAsync(vals, st));
-    if (d_srcs) CU(cudaFreeAsync(d_srcs, st));
-    if (d_sup) CU(cudaFreeAsync(d_sup, st));
-    if (blk_temp) CU(cudaFreeAsync(blk, st));
-    CU(cudaFreeAsync(ctrs, st));
-    if (alpha0) CU(cudaFreeAsync(alpha0, st));
+    // the scratch buffers (vals, sources, counters, alpha0, block statistics) free themselves, stream-ordered
     if (sync) CU(cudaStreamSynchronize(st));
     return WOST_OK;
 }
