@@ -8,7 +8,6 @@ the closing vertex of a loop is never a silhouette vertex (Q4).  There is no CPU
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 import torch

@@ -9,7 +9,7 @@ Dirichlet/Neumann, 3 ``testWostWithSource``, 4 ``testWostVariableCoefficients``,
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field as dc_field
+from dataclasses import dataclass
 from typing import Callable, Optional
 
 import numpy as np

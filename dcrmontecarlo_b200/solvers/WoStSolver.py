@@ -22,13 +22,13 @@ try:
     from ..geometry.Polylines import PolyLines
     from ..utils import torchGradient, torchLaplacian, gridSampleMinMax
     from .. import _native as nat
-    from ..fields import Field, GridField, TermField, as_field
+    from ..fields import Field, TermField, as_field
     from .utils import screened_radius_icdf
 except ImportError:  # pragma: no cover - reference-style sys.path layout (solvers.WoStSolver)
     from geometry.Polylines import PolyLines
     from utils import torchGradient, torchLaplacian, gridSampleMinMax
     import _native as nat
-    from fields import Field, GridField, TermField, as_field
+    from fields import Field, TermField, as_field
     from solvers.utils import screened_radius_icdf
 
 SP_FULL, SP_RATIO, SP_FIELD = nat.SP_FULL, nat.SP_RATIO, nat.SP_FIELD

@@ -6,7 +6,6 @@ legs may import this module; the product package never does.
 from __future__ import annotations
 
 import ctypes as C
-import os
 import subprocess
 from pathlib import Path
 

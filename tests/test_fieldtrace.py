@@ -1,6 +1,5 @@
 """Symbolic tracing of plain callables into exact device fields (dcrmontecarlo_b200/fieldtrace.py)."""
 import numpy as np
-import pytest
 import torch
 
 from dcrmontecarlo_b200.fields import GridField, TermField, as_field
