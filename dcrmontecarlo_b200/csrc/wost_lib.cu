@@ -1397,6 +1397,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, threads, smem));
     if (occ < 1) return fail(WOST_ERR_CUDA, "walk kernel does not fit on an SM");
+    { const int cap = env_int("WOST_MAX_CTAS_PER_SM", 0); if (cap > 0 && occ > cap) occ = cap; }   // experiments: fewer resident warps
     for (long long p0 = 0; p0 < n_pts; p0 += pts_per_pass) {
         const long long np = std::min(pts_per_pass, (long long)n_pts - p0);
         const long long total = np * W;
