@@ -1014,6 +1014,15 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
     if (wost_device_count() <= 0) return fail(WOST_ERR_CUDA, "no CUDA device available (libwost has no CPU fallback)");
     DeviceGuard g(device);
     if (!g.ok) return fail(WOST_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
+    {   // Scratch memory comes from the device's stream-ordered pool.  By default the pool hands everything back to the
+        // driver at every synchronisation, so a caller that reads results on the host (a sync per solve) would pay a
+        // 64 MiB cudaMalloc / cudaFree pair per call, with milliseconds of jitter: keep freed blocks cached instead.
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     // volatile: keep the host compiler from contracting these into FMAs — the tables must hold exactly the
     // fp32 values torch computes for u = b - a and u.u (geometry/PolylinesSimple.py:37,42)
     std::vector<float4> ds(2 * (size_t)(nd - 1)), ns(nn ? 2 * (size_t)(nn - 1) : 0);
