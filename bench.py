@@ -213,16 +213,14 @@ def main():
     sync_all()
     ms = ev0.elapsed_time(ev1)
     my_steps = int(sum(int(o[0]) for o in outs))
-    # the clocks belong to the device-timed region; NVML polling during the wall-clock-timed arm below would contend with
-    # its CUDA API calls (measured: sporadic 30-200 ms stalls)
+    # the clocks belong to the device-timed region; NVML polling stays out of the host-timed arm below
     clocks = sampler.stop()
 
     # ---- end-to-end arm: host buffers through the C ABI -----------------------------------------------
     for it in range(args.warmup):
         step_e2e(it)
-    # Three passes of K steps, the fastest one counts: this arm is timed on the host clock, and on a shared box a pass now
-    # and then catches stalls of 100+ ms while the device-timed arm above stays within 1 % (seen with and without the NVML
-    # sampler, the collector, the memory pool's release threshold); all passes are reported.
+    # Three passes of K steps, the fastest one counts and all are reported: this arm is timed on the host clock, so it sees
+    # what the device-timed arm above does not (an unlucky scheduling of this process, a collector pause).
     import gc
     gc.collect(); gc.disable()                                           # no collector pauses inside the host-timed region
     e2e_passes = []

@@ -798,7 +798,8 @@ template <typename T>
 struct Scratch {
     T* p = nullptr; cudaStream_t st = nullptr;
     int alloc(size_t n, cudaStream_t s) { st = s; CU(cudaMallocAsync((void**)&p, n * sizeof(T), s)); return 0; }
-    ~Scratch() { if (p) cudaFreeAsync(p, st); }
+    int release() { if (p) { T* q = p; p = nullptr; CU(cudaFreeAsync(q, st)); } return 0; }
+    ~Scratch() { if (p) cudaFreeAsync(p, st); }                         // error paths
     Scratch() = default;
     Scratch(const Scratch&) = delete;
     Scratch& operator=(const Scratch&) = delete;
@@ -1014,15 +1015,6 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
     if (wost_device_count() <= 0) return fail(WOST_ERR_CUDA, "no CUDA device available (libwost has no CPU fallback)");
     DeviceGuard g(device);
     if (!g.ok) return fail(WOST_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
-    {   // Scratch memory comes from the device's stream-ordered pool.  By default the pool hands everything back to the
-        // driver at every synchronisation, so a caller that reads results on the host (a sync per solve) would pay a
-        // 64 MiB cudaMalloc / cudaFree pair per call, with milliseconds of jitter: keep freed blocks cached instead.
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
     // volatile: keep the host compiler from contracting these into FMAs — the tables must hold exactly the
     // fp32 values torch computes for u = b - a and u.u (geometry/PolylinesSimple.py:37,42)
     std::vector<float4> ds(2 * (size_t)(nd - 1)), ns(nn ? 2 * (size_t)(nn - 1) : 0);
@@ -1447,7 +1439,10 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (out_walk_vals && vals_temp) sync = true;
     if ((rc = s_pts.finish()) || (rc = s_icdf.finish()) || (rc = s_maj.finish()) || (rc = s_mean.finish()) || (rc = s_m2.finish()) || (rc = s_blk.finish()) ||
         (rc = s_steps.finish()) || (rc = s_trace.finish()) || (rc = s_tlen.finish())) return rc;
-    // the scratch buffers (vals, sources, counters, alpha0, block statistics) free themselves, stream-ordered
+    // Release the scratch BEFORE the synchronisation (the destructors only cover the error paths): with the frees queued
+    // after it, host-side callers (a sync per solve) saw their calls jitter between 10 and 40 ms; this order is steady.
+    if ((rc = vals_s.release()) || (rc = srcs_s.release()) || (rc = sup_s.release()) || (rc = blk_s.release()) ||
+        (rc = ctrs_s.release()) || (rc = alpha0_s.release())) return rc;
     if (sync) CU(cudaStreamSynchronize(st));
     return WOST_OK;
 }
