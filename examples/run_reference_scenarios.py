@@ -51,7 +51,7 @@ def main():
             err = (u - exact).abs()
             line += f"  mean|err| {err.mean():.5f}  max|err| {err.max():.5f}  RMSE {torch.sqrt((err ** 2).mean()):.5f}"
         else:
-            line += "  u = " + " ".join(f"{v:.4f}" for v in u[:9].tolist())
+            line += "  u = " + " ".join(f"{v:.4g}" for v in u[:9].tolist())
         print(line)
 
 
