@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(256, 4) walk_kernel(const WalkArgs a) {
                 theta = (u24(w0) * 2.0f) * 3.14159274101257324f;                        // :226
                 if (NEU && onB) theta = theta / 2.0f + phi_n;                           // :227-228 (Q2)
             }
-            sincosf(theta, &dy, &dx);                                                   // :230-232
+            if (PHYS) sincosf(theta, &dy, &dx);
+            else wm_sincosf_small(theta, &dy, &dx);                                     // :230-232 (|theta| < 10)
             if (NEU) {
                 if (PHYS) { ex = dx; ey = dy; ox = x; oy = y; }
                 else {

@@ -6,12 +6,27 @@
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC (oracle/Makefile).
  */
 #include "wost_oracle.h"
+#include "../include/wost_math.h"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+/* ------------------------------------------------------------------------------------------
+ * Elementary functions.  Default: include/wost_math.h — explicit fp32 arithmetic that the CUDA kernel evaluates
+ * identically, so Philox-mode walks can be compared bit for bit.  g_libm = 1 (set for the duration of an ORC_RNG_MT
+ * solve, or by orc_set_libm): glibc's expf/sinf/cosf, as close as C gets to the torch calls of the reference; that is
+ * the configuration pinned against the reference fixtures.
+ * ---------------------------------------------------------------------------------------- */
+static int g_libm = 0;
+void orc_set_libm(int on) { g_libm = on; }
+static inline float o_expf(float x) { return g_libm ? expf(x) : wm_expf(x); }
+static inline float o_smooth_step(float a) { return g_libm ? 1.0f / (1.0f + expf(a)) : wm_smooth_step(a); }
+static inline void o_sincosf(float a, float* sn, float* cs) {
+    if (g_libm) { *sn = sinf(a); *cs = cosf(a); } else wm_sincosf(a, sn, cs);
+}
 
 /* ------------------------------------------------------------------------------------------
  * RNG streams
@@ -206,7 +221,7 @@ static jet_t term_jet(const orc_term_t* t, float x, float y) {
         /* utils.py:123-129 torch_smooth_circle: sigmoid(-k (|x-c| - R)) */
         float ddx = x - t->cx, ddy = y - t->cy;
         float rho = norm2f(ddx, ddy);
-        float s = 1.0f / (1.0f + expf(t->q * (rho - t->R)));
+        float s = o_smooth_step(t->q * (rho - t->R));
         float s1 = -t->q * s * (1.0f - s);
         float s2 = t->q * t->q * s * (1.0f - s) * (1.0f - 2.0f * s);
         float inv = rho > 0.0f ? 1.0f / rho : 0.0f;
@@ -226,7 +241,7 @@ static jet_t term_jet(const orc_term_t* t, float x, float y) {
     }
     if (t->q != 0.0f) {
         jet_t e; float ddx = x - t->cx, ddy = y - t->cy, d2 = ddx * ddx + ddy * ddy;
-        e.v = expf(-t->q * d2); e.gx = -2.0f * t->q * ddx * e.v; e.gy = -2.0f * t->q * ddy * e.v;
+        e.v = o_expf(-t->q * d2); e.gx = -2.0f * t->q * ddx * e.v; e.gy = -2.0f * t->q * ddy * e.v;
         e.l = e.v * (4.0f * t->q * t->q * d2 - 4.0f * t->q);
         r = jet_mul(r, e);
     }
@@ -234,7 +249,7 @@ static jet_t term_jet(const orc_term_t* t, float x, float y) {
         int kind = k ? t->t2 : t->t1;
         if (kind == ORC_TRIG_NONE) continue;
         float wx = k ? t->w2x : t->w1x, wy = k ? t->w2y : t->w1y, p = k ? t->p2 : t->p1;
-        float a = wx * x + wy * y + p, sn = sinf(a), cs = cosf(a);
+        float a = wx * x + wy * y + p, sn, cs; o_sincosf(a, &sn, &cs);
         jet_t g; float w2 = wx * wx + wy * wy;
         if (kind == ORC_TRIG_SIN) { g.v = sn; g.gx = cs * wx; g.gy = cs * wy; g.l = -sn * w2; }
         else { g.v = cs; g.gx = -sn * wx; g.gy = -sn * wy; g.l = -cs * w2; }
@@ -246,15 +261,13 @@ static jet_t term_jet(const orc_term_t* t, float x, float y) {
 static float term_value(const orc_term_t* t, float x, float y) {
     if (t->kind == ORC_TERM_SIGMOID_CIRCLE) {
         float rho = norm2f(x - t->cx, y - t->cy);
-        return t->A * (1.0f / (1.0f + expf(t->q * (rho - t->R))));
+        return t->A * o_smooth_step(t->q * (rho - t->R));
     }
     float v = t->A;
     if (t->px | t->py) v *= ipowf(x, t->px) * ipowf(y, t->py);
-    if (t->q != 0.0f) { float ddx = x - t->cx, ddy = y - t->cy; v *= expf(-t->q * (ddx * ddx + ddy * ddy)); }
-    if (t->t1 == ORC_TRIG_SIN) v *= sinf(t->w1x * x + t->w1y * y + t->p1);
-    else if (t->t1 == ORC_TRIG_COS) v *= cosf(t->w1x * x + t->w1y * y + t->p1);
-    if (t->t2 == ORC_TRIG_SIN) v *= sinf(t->w2x * x + t->w2y * y + t->p2);
-    else if (t->t2 == ORC_TRIG_COS) v *= cosf(t->w2x * x + t->w2y * y + t->p2);
+    if (t->q != 0.0f) { float ddx = x - t->cx, ddy = y - t->cy; v *= o_expf(-t->q * (ddx * ddx + ddy * ddy)); }
+    if (t->t1 != ORC_TRIG_NONE) { float sn, cs; o_sincosf(t->w1x * x + t->w1y * y + t->p1, &sn, &cs); v *= t->t1 == ORC_TRIG_SIN ? sn : cs; }
+    if (t->t2 != ORC_TRIG_NONE) { float sn, cs; o_sincosf(t->w2x * x + t->w2y * y + t->p2, &sn, &cs); v *= t->t2 == ORC_TRIG_SIN ? sn : cs; }
     return v;
 }
 
@@ -471,10 +484,9 @@ static void greens_norm_pair(const orc_params_t* p, float r, int r_is_rmin, doub
             *sbgn = (float)sb * *gn;
         }
     } else {
-        float zf = r * (float)sqrt(sb);
-        double m1 = zf > 21.0f ? 0.0 : i0_minus_1((double)zf);
-        double Q = zf > 21.0f ? 1.0 : m1 / (1.0 + m1);               /* 1 - 1/I0 without cancellation; 1 to fp32 beyond z = 21 (and no inf/inf) */
-        *sbgn = (float)Q; *gn = (float)(Q / sb);
+        /* the kernel's arithmetic: fp32 throughout, 1 - 1/I0 from include/wost_math.h */
+        *sbgn = wm_interior_probability(r * (float)sqrt(sb));
+        *gn = *sbgn * (float)(1.0 / sb);
     }
 }
 
@@ -508,7 +520,9 @@ static float run_walk(const orc_params_t* p, walk_rng_t* g, float x0, float y0, 
         float theta = (u_theta * 2.0f) * 3.14159274101257324f;       /* :226 fp32 */
         if (onB && has_neu) theta = theta / 2.0f + (p->atan2_fn ? p->atan2_fn(ny, nx) : atan2f(ny, nx));   /* :227-228 (Q2) */
         float dx, dy;                                                /* :230-232 */
-        if (p->sincos_fn) p->sincos_fn(theta, &dx, &dy); else { dx = cosf(theta); dy = sinf(theta); }
+        if (p->sincos_fn) p->sincos_fn(theta, &dx, &dy);
+        else if (g->mode == ORC_RNG_MT) { dx = cosf(theta); dy = sinf(theta); }
+        else wm_sincosf_small(theta, &dy, &dx);
 
         float qx, qy;                                                /* next_point */
         if (has_neu) {
@@ -789,7 +803,8 @@ int orc_solve(const orc_params_t* p, const float* pts, int64_t n_pts,
     int64_t steps_sum = 0;
     if (p->compat_mode == 1 && (p->rng_mode != ORC_RNG_PHILOX || (p->delta && !(p->sigma_bar > 0.0f)))) return -1;   /* physical: Philox only */
     if (p->rng_mode == ORC_RNG_MT) {
-        /* one sequential stream over all points and walks, like the reference */
+        /* one sequential stream over all points and walks, like the reference; libm / torch elementary functions */
+        const int libm_before = g_libm; g_libm = 1;
         mt_t torch_rng, np_rng; mt_seed(&torch_rng, (uint32_t)p->seed); mt_seed(&np_rng, (uint32_t)p->seed_numpy);
         walk_rng_t g; memset(&g, 0, sizeof g);
         g.mode = ORC_RNG_MT; g.torch_rng = &torch_rng; g.np_rng = &np_rng;
@@ -810,6 +825,7 @@ int orc_solve(const orc_params_t* p, const float* pts, int64_t n_pts,
             if (m2) { double mu = s / (double)W; m2[pi] = s2 - (double)W * mu * mu; if (m2[pi] < 0) m2[pi] = 0; }
         }
         free(g.cache);
+        g_libm = libm_before;
     } else {
         int nt = p->n_threads;
 #ifdef _OPENMP

@@ -19,7 +19,7 @@ SP_FULL, SP_RATIO, SP_FIELD = 0, 1, 2
 
 
 def build(force: bool = False) -> Path:
-    src = [HERE / "wost_oracle.c", HERE / "wost_oracle.h"]
+    src = [HERE / "wost_oracle.c", HERE / "wost_oracle.h", HERE.parent / "include" / "wost_math.h"]
     if force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in src):
         subprocess.check_call(["make", "-s", "-C", str(HERE), "libwost_oracle.so"] + (["-B"] if force else []))
     return LIB_PATH

@@ -45,23 +45,25 @@ hdr = rows[hi]
 data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
 assert len(data) == len(lines), (len(data), len(lines), "report and library are different builds")
 ix = {h: i for i, h in enumerate(hdr)}
-inst, samp, noinst = collections.Counter(), collections.Counter(), collections.Counter()
+inst, samp, noinst, tinst = collections.Counter(), collections.Counter(), collections.Counter(), collections.Counter()
 ops = collections.Counter()
 for r, loc in zip(data, lines):
     n = int(r[ix["Instructions Executed"]])
     inst[loc] += n
+    tinst[loc] += int(r[ix["Thread Instructions Executed"]])
     samp[loc] += int(r[ix["# Samples"]])
     noinst[loc] += int(r[ix["stall_no_inst"]])
     m = re.match(r"\s*(@!?U?P\d\s+)?([A-Z0-9_.]+)", r[1])
     ops[m.group(2).split(".")[0] if m else "?"] += n
 ti, ts = sum(inst.values()), sum(samp.values())
 src = {}
-print("total warp instr", ti, " stall samples", ts, " no_inst share %.1f%%" % (100.0 * sum(noinst.values()) / max(ts, 1)))
+print("total warp instr", ti, " stall samples", ts, " no_inst share %.1f%%" % (100.0 * sum(noinst.values()) / max(ts, 1)),
+      " avg active lanes %.2f" % (sum(tinst.values()) / max(ti, 1)))
 for loc, n in inst.most_common(top):
     f, l = loc
     if f not in src:
         p = next(iter(ROOT.rglob(f)), None)
         src[f] = p.read_text().splitlines() if p else []
     text = src[f][l - 1].strip() if 0 < l <= len(src[f]) else ""
-    print("%5.1f%% instr %5.1f%% samp  %s:%4d  %s" % (100.0 * n / ti, 100.0 * samp[loc] / ts, f, l, text[:100]))
+    print("%5.1f%% instr %4.1f lanes %5.1f%% samp  %s:%4d  %s" % (100.0 * n / ti, tinst[loc] / max(n, 1), 100.0 * samp[loc] / ts, f, l, text[:100]))
 print({k: round(100.0 * v / ti, 1) for k, v in ops.most_common(25)})
