@@ -48,7 +48,8 @@ class SolveParams(C.Structure):
                 ("sp_mode", C.c_int32), ("sigma_bar", C.c_float), ("screened_icdf", C.c_void_p), ("icdf_len", C.c_int32),
                 ("seed", C.c_uint64), ("point_index_base", C.c_int64), ("walk_offset", C.c_int64), ("compat_mode", C.c_int32),
                 ("majorant_levels", C.c_int32), ("majorant", C.c_void_p),
-                ("majorant_x0", C.c_float), ("majorant_y0", C.c_float), ("majorant_dx", C.c_float), ("majorant_dy", C.c_float)]
+                ("majorant_x0", C.c_float), ("majorant_y0", C.c_float), ("majorant_dx", C.c_float), ("majorant_dy", C.c_float),
+                ("jit", C.c_int32)]
 
 
 EXPORTS = {
@@ -74,7 +75,11 @@ EXPORTS = {
     "wost_geom_intersect": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wost_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "wost_jit_stats": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "wost_jit_last_note": (C.c_char_p, []),
+    "wost_jit_offline": (C.c_int, [C.POINTER(C.POINTER(FieldDesc))] + [C.c_int32] * 11 + [C.c_char_p, C.c_char_p]),
 }
+JIT = {"auto": 0, "on": 1, "off": 2}
 
 _lib = None
 
@@ -144,22 +149,28 @@ class Scene:
         self._fin = weakref.finalize(self, lib().wost_scene_destroy, h)
 
 
+def field_desc(field):
+    """wost_field_desc_t of a fields.Field, plus the arrays it points into (keep them alive while the struct is used)."""
+    desc = field.describe()
+    terms = np.ascontiguousarray(desc["terms"])
+    assert terms.dtype.itemsize == C.sizeof(_Term), "term layout mismatch with wost_term_t"
+    grid = None if desc["grid"] is None else host_f32(desc["grid"])
+    d = FieldDesc()
+    d.kind, d.n_terms, d.c0, d.mask_kind = int(desc["kind"]), len(terms), float(desc["c0"]), int(desc["mask_kind"])
+    for i in range(4):
+        d.mask[i] = float(desc["mask"][i])
+    d.outside = float(desc["outside"])
+    d.nx, d.ny, d.x0, d.y0, d.dx, d.dy = int(desc["nx"]), int(desc["ny"]), desc["x0"], desc["y0"], desc["dx"], desc["dy"]
+    d.terms = terms.ctypes.data if len(terms) else None
+    d.grid = grid.ctypes.data if grid is not None else None
+    return d, terms, grid
+
+
 class DeviceField:
     """wost_field_t handle built from a fields.Field description."""
 
     def __init__(self, field, device: int):
-        desc = field.describe()
-        self._terms = np.ascontiguousarray(desc["terms"])
-        assert self._terms.dtype.itemsize == C.sizeof(_Term), "term layout mismatch with wost_term_t"
-        self._grid = None if desc["grid"] is None else host_f32(desc["grid"])
-        d = FieldDesc()
-        d.kind, d.n_terms, d.c0, d.mask_kind = int(desc["kind"]), len(self._terms), float(desc["c0"]), int(desc["mask_kind"])
-        for i in range(4):
-            d.mask[i] = float(desc["mask"][i])
-        d.outside = float(desc["outside"])
-        d.nx, d.ny, d.x0, d.y0, d.dx, d.dy = int(desc["nx"]), int(desc["ny"]), desc["x0"], desc["y0"], desc["dx"], desc["dy"]
-        d.terms = self._terms.ctypes.data if len(self._terms) else None
-        d.grid = self._grid.ctypes.data if self._grid is not None else None
+        d, self._terms, self._grid = field_desc(field)
         h = C.c_void_p(0)
         check(lib().wost_field_create(C.byref(d), int(device), C.byref(h)))
         self.handle, self.device = h, int(device)
@@ -206,7 +217,7 @@ def _set_majorant(prm, majorant):
 def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: float, *, delta: bool = False,
           sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0, point_index_base: int = 0,
           walk_offset: int = 0, want_block_stats: bool = False, want_walk_vals: bool = False, n_trace: int = 0,
-          trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference", majorant=None):
+          trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference", majorant=None, jit: str = "auto"):
     """One wost_solve call.  ``pts`` may be a host array/tensor or a CUDA tensor on the scene's device.
     With ``device_outputs`` the results stay on the device as torch tensors (stream-ordered, no sync)."""
     dev = scene.device
@@ -225,6 +236,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
     prm.compat_mode = COMPAT[compat]
+    prm.jit = JIT[jit]
     maj_keep = _set_majorant(prm, majorant)
 
     if device_outputs:
@@ -258,7 +270,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
 def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int, max_steps: int, eps: float, *,
                        delta: bool = False, sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0,
                        point_index_base: int = 0, walk_offset: int = 0, want_block_stats: bool = False,
-                       device_outputs: bool = False, compat: str = "reference", majorant=None):
+                       device_outputs: bool = False, compat: str = "reference", majorant=None, jit: str = "auto"):
     """One wost_solve_multi_source call: shared walks, one estimate per (source, point).  ``sources`` is a list of
     DeviceField.  Returns mean / m2 of shape (S, P)."""
     dev = scene.device
@@ -277,6 +289,7 @@ def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int,
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
     prm.compat_mode = COMPAT[compat]
+    prm.jit = JIT[jit]
     maj_keep = _set_majorant(prm, majorant)
     handles = (C.c_void_p * S)(*[s.handle for s in sources])
     if device_outputs:
@@ -309,6 +322,31 @@ def merge_block_stats(block_stats, n_walks: int, device: int):
         mean, m2 = np.empty(P, np.float64), np.empty(P, np.float64)
     check(lib().wost_merge_block_stats(ptr(b), P, int(n_walks), int(device), ptr(mean), ptr(m2), current_stream(device)))
     return mean, m2
+
+
+def jit_stats():
+    """(kernels compiled by NVRTC, cache hits, solves that ran a specialised kernel)"""
+    a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    check(lib().wost_jit_stats(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def jit_last_note() -> str:
+    return lib().wost_jit_last_note().decode(errors="replace")
+
+
+def jit_offline(fields: dict, *, neu, src, delta, trace=False, phys=False, big=False, multi=False, sp_mode=0, min_blocks=4,
+                n_dseg=-1, n_nseg=-1, arch="sm_100a", prefix="wost_walk_jit"):
+    """Developer diagnostic (no GPU needed): compile the specialised kernel for ``fields`` (dict g / f / alpha / sigma /
+    sigma_prime -> fields.Field or None) and write ``prefix``.cu / .cubin."""
+    keep, arr = [], (C.POINTER(FieldDesc) * 5)()
+    for i, k in enumerate(("g", "f", "alpha", "sigma", "sigma_prime")):
+        if fields.get(k) is not None:
+            d = field_desc(fields[k]); keep.append(d)
+            arr[i] = C.pointer(d[0])
+    check(lib().wost_jit_offline(arr, int(neu), int(src), int(delta), int(trace), int(phys), int(big), int(multi), int(sp_mode),
+                                 int(min_blocks), int(n_dseg), int(n_nseg), arch.encode(), str(prefix).encode()))
+    return lib().wost_last_error().decode()
 
 
 def fp32_peak(device: int = 0):

@@ -52,7 +52,7 @@ class WostSolver_2D:
                  neumannBoundary: PolyLines = None, source: callable = None, sigma: callable = None,
                  alpha: callable = None, *, field_resolution: int = 257, sigma_prime_resolution: int = 65,
                  sigma_prime_mode: str = "auto", compat: str = "reference", field_tolerance: float | None = 1e-3,
-                 majorant_resolution: int = 256):
+                 majorant_resolution: int = 256, jit: str = "auto"):
         """``sigma_prime_mode``: ``"auto"`` differentiates the coefficients like the reference and falls back to
         ``sigma/alpha`` when that fails; ``"ratio"`` forces the fallback — what the reference ends up with for
         callables that wrap their result in ``torch.tensor(...)`` (tests/testWostVariableCoefficients.py:49,57,
@@ -67,6 +67,11 @@ class WostSolver_2D:
         estimator is biased, Q8/Q9/Q13) and is validated against analytic solutions instead."""
         if compat not in nat.COMPAT:
             raise ValueError("compat must be 'reference' or 'physical'")
+        if jit not in nat.JIT:
+            raise ValueError("jit must be 'auto', 'on' or 'off'")
+        # "auto": jobs of >= 2^18 walks run a kernel compiled for this solver's own fields (NVRTC, ~0.3 s once per field
+        # set, cached); "on" / "off" force / forbid it.  Bit-identical results either way.
+        self.jit = jit
         self.compat = compat
         # physical mode with variable coefficients: cells per side of the spatially varying majorant (a power of two;
         # 0 = one majorant for the whole domain)
@@ -327,7 +332,7 @@ class WostSolver_2D:
     # ------------------------------------------------------------------------------------------------
     def solve_raw(self, solvePoints, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None, point_index_base=0,
                   walk_offset=0, want_block_stats=False, want_walk_vals=False, n_trace=0, trace_cap=0,
-                  device_outputs=False, device=None):
+                  device_outputs=False, device=None, jit=None):
         """One kernel pass over ``solvePoints`` on one device; returns the raw statistics dict
         (mean, m2, steps, optional block_stats / walk_vals / trace).  Building block of :meth:`solve`
         and of the multi-GPU driver (:mod:`dcrmontecarlo_b200.distributed`)."""
@@ -341,12 +346,12 @@ class WostSolver_2D:
                         sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
                         point_index_base=point_index_base, walk_offset=walk_offset, want_block_stats=want_block_stats,
                         want_walk_vals=want_walk_vals, n_trace=n_trace, trace_cap=trace_cap, device_outputs=device_outputs,
-                        compat=self.compat, majorant=self._device_majorant(device))
+                        compat=self.compat, majorant=self._device_majorant(device), jit=jit or self.jit)
         res["seed"] = seed
         return res
 
     def solve_multi_source(self, solvePoints, sources, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None,
-                           want_block_stats=False, device_outputs=False, device=None):
+                           want_block_stats=False, device_outputs=False, device=None, jit=None):
         """Shared-walk solve for many source terms (not in the reference, which re-walks per source): the walk does not
         depend on ``f``, so one set of walks gives the estimate for every source in ``sources`` (callables or fields).
         Returns ``mean`` / ``m2`` of shape ``(len(sources), P)``; row ``s`` equals what :meth:`solve_raw` returns with
@@ -361,7 +366,7 @@ class WostSolver_2D:
                                      delta=self.use_delta_tracking, sp_mode=self.sp_mode,
                                      sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
                                      want_block_stats=want_block_stats, device_outputs=device_outputs, compat=self.compat,
-                                     majorant=self._device_majorant(device))
+                                     majorant=self._device_majorant(device), jit=jit or self.jit)
         res["seed"] = seed
         return res
 

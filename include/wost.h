@@ -22,13 +22,15 @@
  */
 #ifndef WOST_H
 #define WOST_H
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define WOST_VERSION 101   /* major*10000 + minor*100 + patch */
+#define WOST_VERSION 200   /* major*10000 + minor*100 + patch */
 
 typedef enum {
     WOST_OK = 0,
@@ -125,10 +127,17 @@ typedef struct {
     int32_t majorant_levels;
     const float* majorant;
     float majorant_x0, majorant_y0, majorant_dx, majorant_dy;
+    /* Per-solver specialised kernel: the fields of this solve compiled into the walk kernel with NVRTC (cached per field
+     * set), instead of the interpreter over field descriptors.  Results are bit-identical either way.
+     * 0 = auto (jobs of >= 2^18 walks, or whenever the kernel is compiled already), 1 = always (error if NVRTC is
+     * unavailable), 2 = never.  The environment variable WOST_JIT (0 / 1) overrides; WOST_JIT_CACHE=<dir> keeps compiled
+     * kernels on disk. */
+    int32_t jit;
 } wost_solve_params_t;
 
 #define WOST_WALK_BLOCK 1024   /* walks per deterministic reduction block */
 
+#ifndef __CUDACC_RTC__   /* the entry points are host functions: hidden from the run-time (NVRTC) compile of the kernels */
 /* ---- library ------------------------------------------------------------------------------- */
 int wost_version(void);
 const char* wost_last_error(void);
@@ -204,8 +213,19 @@ int wost_geom_intersect(const wost_scene_t* scene, int32_t which, const float* p
                         const float* r, int64_t B,
                         float* out_pt, float* out_nrm, uint8_t* out_found, int32_t* out_seg, void* stream);
 
+/* specialised-kernel bookkeeping: kernels compiled by NVRTC so far, cache hits, solves that ran a specialised kernel;
+ * wost_jit_last_note() says why the last solve did not ("" if it did) */
+int wost_jit_stats(int64_t* out_compiled, int64_t* out_cache_hits, int64_t* out_launches);
+const char* wost_jit_last_note(void);
+/* developer diagnostic, no device needed: generate + compile the specialised kernel for five field descriptors
+ * (g, f, alpha, sigma, sigma_prime; NULL = absent) and write <prefix>.cu / <prefix>.cubin for cuobjdump */
+int wost_jit_offline(const wost_field_desc_t* const descs[5], int32_t neu, int32_t src, int32_t delta, int32_t trace,
+                     int32_t phys, int32_t big, int32_t multi, int32_t sp_mode, int32_t min_blocks,
+                     int32_t n_dirichlet_seg /* -1: run-time sizes */, int32_t n_neumann_seg, const char* arch, const char* prefix);
+
 /* FP32 FMA-chain microbenchmark: measured non-tensor fp32 TFLOP/s of the device (roofline denominator) */
 int wost_fp32_peak(int32_t device, double* out_tflops, double* out_sm_mhz_effective);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

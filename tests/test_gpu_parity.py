@@ -818,3 +818,71 @@ def test_resumable_estimate_equals_uninterrupted_run(tmp_path):
     assert np.allclose(se, np.sqrt(full["m2"] / 4999 / 5000), rtol=1e-12)
     with pytest.raises(ValueError):
         resumed.add_walks(10)                                                # 5000 is not on a block boundary
+
+
+# ---- per-solver specialised kernels (NVRTC) -----------------------------------------------------------------------------
+@pytest.mark.parametrize("key", CFGS + ["phys_varcoef_neumann", "phys_poisson"])
+def test_jit_kernels_equal_static_kernels_bitwise(key):
+    """The kernel compiled for a solver's own fields (wost_jit.inc: the interpreter's functions with every term a
+    compile-time constant) must reproduce the statically compiled interpreter kernel bit for bit: per-walk totals, step
+    counts, traces."""
+    s = (sc.ALL.get(key) or sc.PHYSICAL.get(key) or sc.PHYSICAL_VARCOEF[key])()
+    solver = s.make_solver()
+    pts = s.points[:: max(1, len(s.points) // 24)][:24].contiguous()
+    W = 200
+    before = nat.jit_stats()
+    a = solver.solve_raw(pts, W, s.max_steps, s.eps, seed=99, want_walk_vals=True, n_trace=64, trace_cap=6, jit="on")
+    assert nat.jit_last_note() == "" and nat.jit_stats()[2] == before[2] + 1
+    b = solver.solve_raw(pts, W, s.max_steps, s.eps, seed=99, want_walk_vals=True, n_trace=64, trace_cap=6, jit="off")
+    assert nat.jit_last_note() != "" and nat.jit_stats()[2] == before[2] + 1
+    assert np.array_equal(bits(a["walk_vals"]), bits(b["walk_vals"]))
+    assert int(a["steps"][0]) == int(b["steps"][0])
+    assert np.array_equal(a["trace_len"], b["trace_len"])
+    assert np.array_equal(bits(np.nan_to_num(a["trace"], nan=-1.0)), bits(np.nan_to_num(b["trace"], nan=-1.0)))
+    assert np.array_equal(a["mean"], b["mean"]) and np.array_equal(a["m2"], b["m2"])
+    # no trace, larger job: the throughput instantiation
+    a = solver.solve_raw(pts, 1500, s.max_steps, s.eps, seed=5, want_walk_vals=True, jit="on")
+    b = solver.solve_raw(pts, 1500, s.max_steps, s.eps, seed=5, want_walk_vals=True, jit="off")
+    assert np.array_equal(bits(a["walk_vals"]), bits(b["walk_vals"])) and int(a["steps"][0]) == int(b["steps"][0])
+
+
+def test_jit_random_fields_equal_static_and_oracle():
+    """Random fields over the whole term algebra (monomials, Gaussians, trig factors, smooth circles, masks):
+    specialised kernel == interpreter kernel == oracle, bit for bit."""
+    from dcrmontecarlo_b200.fields import make_circle_term
+
+    rng = np.random.default_rng(7)
+    s = sc.cfg4()
+
+    def rand_terms(n):
+        terms = []
+        for _ in range(n):
+            kind = rng.integers(0, 4)
+            c = (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)))
+            if kind == 0:
+                terms.append(make_term(A=float(rng.normal()), px=int(rng.integers(0, 4)), py=int(rng.integers(0, 4))))
+            elif kind == 1:
+                terms.append(make_term(A=float(rng.normal()), q=float(rng.uniform(0.2, 3.0)), center=c, px=int(rng.integers(0, 2))))
+            elif kind == 2:
+                terms.append(make_term(A=float(rng.normal()), trig1=("sin", float(rng.normal() * 3), float(rng.normal() * 3), float(rng.normal())),
+                                       trig2=("cos", float(rng.normal() * 2), 0.0, 0.3) if rng.random() < 0.5 else None))
+            else:
+                terms.append(make_circle_term(float(rng.uniform(0.1, 1.0)), c, float(rng.uniform(0.2, 0.8)), k=float(rng.uniform(5, 60))))
+        return terms
+
+    alphas = [TermField(4.0, [make_term(A=0.5, q=1.0), make_circle_term(0.7, (0.3, -0.2), 0.5, k=25.0)]),
+              TermField(5.0, [make_term(A=0.3, px=1), make_term(A=0.2, trig1=("sin", 2.0, 1.0, 0.1))]),
+              TermField(3.0, [make_term(A=0.1, px=2, py=1), make_term(A=0.4, q=0.5, center=(0.5, 0.5))])]
+    for trial, alpha in enumerate(alphas):
+        sigma = TermField(1.0, rand_terms(2))
+        f = TermField(0.0, rand_terms(4)).masked_disc((0.0, 0.0), 1.4, outside=0.0)
+        g = TermField(0.2, rand_terms(3))
+        solver = WostSolver_2D(PolyLinesSimple(s.dirichlet), g, PolyLinesSimple(s.neumann), source=f, sigma=sigma, alpha=alpha)
+        pts = s.points[::60][:10].contiguous()
+        a = solver.solve_raw(pts, 300, 300, 1e-3, seed=trial, want_walk_vals=True, jit="on")
+        b = solver.solve_raw(pts, 300, 300, 1e-3, seed=trial, want_walk_vals=True, jit="off")
+        assert np.array_equal(bits(a["walk_vals"]), bits(b["walk_vals"])), trial
+        icdf = solver._cache[("icdf", float(solver.sigma_bar), nat.current_device())].cpu().numpy()
+        prob = orc.Problem(s.dirichlet, s.neumann, g=g, f=f, alpha=alpha, sigma=sigma, sigma_bar=solver.sigma_bar, sp_mode=solver.sp_mode)
+        o = prob.solve(pts, 300, 300, 1e-3, rng_mode=orc.RNG_PHILOX, seed=trial, icdf=icdf, walk_vals=True)
+        assert np.array_equal(bits(a["walk_vals"]), bits(o["walk_vals"])), trial

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = nat.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.wost_version() == 101
+    assert L.wost_version() == 200
     assert L.wost_device_count() >= 0
 
 
@@ -37,7 +37,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(nat._Term) == 64
     assert C.sizeof(nat.FieldDesc) == 80                                    # 60 bytes of scalars, padded to 64, two pointers
     assert C.sizeof(nat.Fields) == 40
-    assert C.sizeof(nat.SolveParams) == 104
+    assert C.sizeof(nat.SolveParams) == 112
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the behaviour WITHOUT a GPU")
@@ -239,3 +239,23 @@ def test_survey_helpers():
     rho, I = 40.0, 1.0
     V = lambda p: -(rho * I / np.pi) * (np.log(np.hypot(p[0] - a[0], p[1])) - np.log(np.hypot(p[0] - b[0], p[1])))   # noqa: E731
     assert geometric_factor_2d(a, b, m, n) * (V(m) - V(n)) / I == pytest.approx(rho)
+
+
+@pytest.mark.parametrize("key", ["cfg1a", "cfg1b", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_specialised_kernel_compiles_without_a_device(key, tmp_path):
+    """wost_jit_offline: the per-solver kernel (NVRTC, wost_jit.inc) compiles for every reference scenario on a CPU-only
+    box; the generated source holds the fields as constants and the cubin is sm_100a code without local-memory spills."""
+    import subprocess
+
+    s = sc.ALL[key]()
+    prefix = tmp_path / f"jit_{key}"
+    note = nat.jit_offline(dict(g=s.g, f=s.f, alpha=s.alpha, sigma=s.sigma), neu=s.neumann is not None, src=s.f is not None,
+                           delta=s.delta, sp_mode=s.sp_mode if s.delta else 0, prefix=prefix,
+                           n_dseg=len(s.dirichlet) - 1, n_nseg=(len(s.neumann) - 1) if s.neumann is not None else 0)
+    assert note.startswith("compiled in")
+    src = prefix.with_suffix(".cu").read_text()
+    assert "struct JitFP" in src and "wost_walk_jit" in src and "term_value_t" in src
+    res = subprocess.run(["cuobjdump", "-res-usage", str(prefix.with_suffix(".cubin"))], capture_output=True, text=True).stdout
+    assert "wost_walk_jit" in res
+    m = re.search(r"REG:(\d+) STACK:(\d+)", res)
+    assert m and int(m.group(1)) <= 64 and int(m.group(2)) == 0, res

@@ -8,6 +8,7 @@ file:line of every instruction.  The two listings are in the same order, so they
 (The library must be the build that was profiled.)
 """
 import collections
+import os
 import csv
 import io
 import re
@@ -21,7 +22,7 @@ rep, kernel = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 
 with tempfile.TemporaryDirectory() as td:
-    subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "dcrmontecarlo_b200" / "libwost.so")], cwd=td, check=True, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("WOST_LIB", str(ROOT / "dcrmontecarlo_b200" / "libwost.so"))], cwd=td, check=True, capture_output=True)
     cubin = next(Path(td).glob("*.cubin"))
     dis = subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True, check=True).stdout
 lines, cur, inside = [], ("?", 0), False

@@ -10,9 +10,11 @@ from dcrmontecarlo_b200 import scenarios as sc  # noqa: E402
 
 name = sys.argv[1]
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+walks_override = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 table = {"cfg1a": (sc.cfg1a, 65536, 256), "cfg1b": (sc.cfg1b, 65536, 64), "cfg2": (sc.cfg2, 65536, 256), "cfg3": (sc.cfg3, 65536, 256),
          "cfg4": (sc.cfg4, 65536, 64), "cfg5_9e": (lambda: sc.cfg5(9), 9, 32768), "cfg5_175e": (lambda: sc.cfg5(175), 175, 4096)}
 mk, n, w = table[name]
+w = walks_override or w
 s = mk()
 pts = s.points.repeat((n + len(s.points) - 1) // len(s.points), 1)[:n].contiguous().cuda()
 solver = s.make_solver()
