@@ -23,6 +23,8 @@ import builtins
 import math
 
 import numpy as np
+import threading
+
 import torch
 
 try:
@@ -494,30 +496,36 @@ def _symbolic(fn) -> TermField:
     return field.masked_box(*mask[1:], outside=outside)
 
 
+_TRACE_LOCK = threading.RLock()
+
+
 def trace_callable(fn, bounds, n_check: int = 32, rtol: float = 2e-5):
     """``fn`` as an exact :class:`TermField`, or ``None`` if it is outside the term algebra or fails the numerical
     check against the callable on ``n_check`` random points of ``bounds = [[xmin, xmax], [ymin, ymax]]``."""
     # `float(expr)` and `torch.tensor(expr)` wrappers (tests/testWostWithSource.py:48, testWostVariableCoefficients.py:49)
     # must let the symbolic value through while tracing: shadow `float` in the callable's globals, patch torch.tensor.
     g = getattr(fn, "__globals__", None)
-    had_float = g is not None and "float" in g
-    old_float = g.get("float") if had_float else None
-    old_tensor = torch.tensor
-    try:
-        if g is not None:
-            g["float"] = _passthrough_float
-        torch.tensor = lambda v, *a, **k: v if isinstance(v, (Sym, Affine)) else old_tensor(v, *a, **k)
+    # the patching below touches process-wide names (torch.tensor, the callable's module globals): one tracer at a time,
+    # and other threads only ever see the pass-through wrappers, which behave like the originals for ordinary values
+    with _TRACE_LOCK:
+        had_float = g is not None and "float" in g
+        old_float = g.get("float") if had_float else None
+        old_tensor = torch.tensor
         try:
-            field = _symbolic(fn)
-        except Exception:                       # _Untraceable, or whatever the callable does with a symbolic point
-            return None
-    finally:
-        torch.tensor = old_tensor
-        if g is not None:
-            if had_float:
-                g["float"] = old_float
-            else:
-                g.pop("float", None)
+            if g is not None:
+                g["float"] = _passthrough_float
+            torch.tensor = lambda v, *a, **k: v if isinstance(v, (Sym, Affine)) else old_tensor(v, *a, **k)
+            try:
+                field = _symbolic(fn)
+            except Exception:                   # _Untraceable, or whatever the callable does with a symbolic point
+                return None
+        finally:
+            torch.tensor = old_tensor
+            if g is not None:
+                if had_float:
+                    g["float"] = old_float
+                else:
+                    g.pop("float", None)
     (x0, x1), (y0, y1) = [[float(b[0]), float(b[1])] for b in bounds]
     gen = torch.Generator().manual_seed(12345)
     mx, my = 0.05 * (x1 - x0), 0.05 * (y1 - y0)                          # a little beyond the box: masks are tested too

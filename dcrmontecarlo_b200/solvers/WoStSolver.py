@@ -99,6 +99,10 @@ class WostSolver_2D:
         self.sp_mode = SP_FULL
         self.last_stats = None
         self._cache: dict = {}
+        # bound methods are new objects on every attribute access: bind the sigma' tabulation callable ONCE so that the
+        # id()-keyed field cache below hits on the second solve
+        self._sp_plain = self._sigma_prime_plain
+        self._probe_pts = None
 
         if sigma is not None or alpha is not None:                      # reference :54-64
             self.sigma = (lambda point: 0.0) if sigma is None else sigma
@@ -260,10 +264,21 @@ class WostSolver_2D:
     # setters (reference :141-157)
     # ------------------------------------------------------------------------------------------------
     def setBoundaryConditions(self, boundaryDirichlet: callable):
+        self._forget(self.boundaryDirichlet)
         self.boundaryDirichlet = boundaryDirichlet
 
     def setSourceTerm(self, source: callable):
+        self._forget(self.source)
         self.source = source
+
+    def invalidate(self):
+        """Drop every cached device field / table (after changing state a coefficient callable closes over)."""
+        self._cache = {k: v for k, v in self._cache.items() if k[0] == "scene"}
+
+    def _forget(self, obj):
+        if obj is not None and not isinstance(obj, Field):
+            for k in [k for k in self._cache if k[0] in ("host", "dev") and k[1] == id(obj)]:
+                del self._cache[k]
 
     # ------------------------------------------------------------------------------------------------
     # device objects
@@ -271,8 +286,35 @@ class WostSolver_2D:
     def _bounds(self):
         return [[float(a), float(b)] for a, b in self.domain_bounds]
 
+    def _probe_points(self):
+        """A few fixed points inside the bounding box at which cached fields are re-checked against their callables."""
+        if self._probe_pts is None:
+            (x0, x1), (y0, y1) = self._bounds()
+            u = torch.tensor([[0.5, 0.5], [0.21, 0.67], [0.83, 0.29], [0.37, 0.11], [0.64, 0.91]], dtype=torch.float32)
+            self._probe_pts = torch.stack([x0 + u[:, 0] * (x1 - x0), y0 + u[:, 1] * (y1 - y0)], dim=1)
+        return self._probe_pts
+
+    def _still_valid(self, obj, field) -> bool:
+        """The reference calls g / f / alpha / sigma live on every step; here a plain callable is traced or tabulated
+        once.  If the state it closes over changed since (a source parameter, an electrode position), the cached device
+        field would silently be stale: compare it with the callable at the probe points before every solve."""
+        if isinstance(obj, Field) or getattr(obj, "__self__", None) is self:
+            return True
+        try:
+            for p in self._probe_points():
+                live = obj(p.clone())
+                live = float(live.detach()) if isinstance(live, torch.Tensor) else float(live)
+                have = float(field(p.reshape(1, 2))[0])
+                if not (abs(live - have) <= 1e-3 * max(1.0, abs(live)) or (live != live and have != have)):
+                    return False
+        except Exception:
+            return True                                                    # cannot be probed (e.g. needs grad): keep
+        return True
+
     def _host_field(self, obj, n=None):
         key = ("host", id(obj), n)
+        if key in self._cache and not self._still_valid(obj, self._cache[key][1]):
+            self._forget(obj)
         if key not in self._cache:
             # sigma' tables (explicit n) evaluate autograd point by point: fixed resolution; everything else is refined
             self._cache[key] = (obj, as_field(obj, bounds=self._bounds(), n=n or self.field_resolution,
@@ -283,8 +325,9 @@ class WostSolver_2D:
         if obj is None:
             return None
         key = ("dev", id(obj), device, n)
-        if key not in self._cache:
-            self._cache[key] = (obj, nat.DeviceField(self._host_field(obj, n), device))
+        host = self._host_field(obj, n)                                    # re-validates the cached field (and may drop it)
+        if key not in self._cache or self._cache[key][2] is not host:
+            self._cache[key] = (obj, nat.DeviceField(host, device), host)
         return self._cache[key][1]
 
     def _scene(self, device):
@@ -305,7 +348,7 @@ class WostSolver_2D:
             alpha = self._dev_field(self.alpha, device) if self._alpha_given else None
             sigma = self._dev_field(self.sigma, device) if self._sigma_given else None
             if self.sp_mode == SP_FIELD:
-                sp = self._dev_field(self._sigma_prime_plain, device, self.sigma_prime_resolution)
+                sp = self._dev_field(self._sp_plain, device, self.sigma_prime_resolution)
             if self.compat != "physical":                                # physical mode samples the radius directly
                 key = ("icdf", float(self.sigma_bar), device)
                 if key not in self._cache:
@@ -380,7 +423,7 @@ class WostSolver_2D:
         if return_history:
             trace_cap = int(min(maxSteps, 4096))
             n_trace = P * int(nWalks)
-            if n_trace * trace_cap * 16 > (1 << 30):
+            if n_trace * (trace_cap + 1) * 32 > (1 << 30):                # (n_trace, trace_cap + 1, 8) float32, host and device
                 raise ValueError("return_history would need more than 1 GiB of trace; lower nWalks, maxSteps or the point count")
         res = self.solve_raw(pts, nWalks, maxSteps, eps, seed=seed, want_walk_vals=return_history, n_trace=n_trace, trace_cap=trace_cap)
         mean = torch.from_numpy(res["mean"])
@@ -390,6 +433,11 @@ class WostSolver_2D:
         out = mean.to(torch.float32).unsqueeze(1).to(pts.device)
         extras = []
         if return_history:
+            if trace_cap < maxSteps and bool((np.asarray(res["trace_len"]) >= trace_cap).any()):
+                import warnings
+
+                warnings.warn(f"return_history: walks longer than {trace_cap} steps are truncated in the history "
+                              "(their estimates are complete)", RuntimeWarning)
             extras.append(self._history(res, pts.reshape(-1, 2), int(nWalks)))
         if return_stats:
             extras.append(self.last_stats)

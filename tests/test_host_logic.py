@@ -259,3 +259,43 @@ def test_specialised_kernel_compiles_without_a_device(key, tmp_path):
     assert "wost_walk_jit" in res
     m = re.search(r"REG:(\d+) STACK:(\d+)", res)
     assert m and int(m.group(1)) <= 64 and int(m.group(2)) == 0, res
+
+
+def test_cached_fields_follow_closure_state_and_setters():
+    """a traced / tabulated callable is cached per solver; if the state it closes over changes between solves the
+    cached field must not be used silently (the reference calls its callables live, solvers/WoStSolver.py:253-256)."""
+    from dcrmontecarlo_b200.geometry.PolylinesSimple import PolyLinesSimple
+    from dcrmontecarlo_b200.solvers.WoStSolver import WostSolver_2D
+
+    state = {"k": 1.0}
+    g = lambda p: state["k"] * p[0]                                              # noqa: E731
+    solver = WostSolver_2D(PolyLinesSimple(sc.square(1.0)), g)
+    q = torch.tensor([[0.5, 0.25]])
+    assert float(solver._host_field(g)(q)[0]) == pytest.approx(0.5)
+    assert solver._host_field(g) is solver._host_field(g)                        # cached while the callable is unchanged
+    state["k"] = 5.0
+    assert float(solver._host_field(g)(q)[0]) == pytest.approx(2.5)              # re-traced, not stale
+    # setters drop the cache entries of the callable they replace
+    n = len(solver._cache)
+    solver.setBoundaryConditions(lambda p: 2.0 * p[1])
+    assert len(solver._cache) < n
+    solver.invalidate()
+    assert all(k[0] == "scene" for k in solver._cache)
+
+
+def test_sigma_prime_table_is_cached_across_solves():
+    """in SP_FIELD mode the sigma' table was keyed on id(bound method) -- a new object on every access -- so
+    every solve re-tabulated it point by point.  The callable is bound once now."""
+    from dcrmontecarlo_b200.geometry.PolylinesSimple import PolyLinesSimple
+    from dcrmontecarlo_b200.solvers.WoStSolver import WostSolver_2D
+
+    s = sc.cfg1b()
+    alpha = lambda p: 2.0 + torch.sqrt(p[0] ** 2 + 1.0) * 0.5 + 0.25 * p[1]      # noqa: E731  (outside the term algebra)
+    solver = WostSolver_2D(PolyLinesSimple(s.dirichlet), s.g, None, source=s.f, alpha=alpha, sigma=s.sigma,
+                           field_resolution=33, sigma_prime_resolution=9)
+    assert solver.sp_mode == nat.SP_FIELD
+    assert solver._sp_plain is solver._sp_plain
+    a = solver._host_field(solver._sp_plain, solver.sigma_prime_resolution)
+    n = len(solver._cache)
+    b = solver._host_field(solver._sp_plain, solver.sigma_prime_resolution)
+    assert a is b and len(solver._cache) == n
