@@ -59,6 +59,7 @@ EXPORTS = {
     "wost_device_count": (C.c_int, []),
     "wost_scene_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "wost_scene_destroy": (C.c_int, [C.c_void_p]),
+    "wost_scene_trim": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "wost_field_create": (C.c_int, [C.POINTER(FieldDesc), C.c_int32, C.POINTER(C.c_void_p)]),
     "wost_field_destroy": (C.c_int, [C.c_void_p]),
     "wost_field_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -147,6 +148,12 @@ class Scene:
         self.handle = h
         self.n_dirichlet, self.n_neumann = len(d), 0 if n is None else len(n)
         self._fin = weakref.finalize(self, lib().wost_scene_destroy, h)
+
+    def trim(self) -> int:
+        """Return the scene's cached device scratch to the driver; returns the number of bytes released."""
+        n = C.c_int64(0)
+        check(lib().wost_scene_trim(self.handle, C.byref(n)))
+        return n.value
 
 
 def field_desc(field):

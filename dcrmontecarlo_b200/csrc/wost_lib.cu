@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -26,6 +27,38 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess)                                                                           \
             return fail(WOST_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
     } while (0)
+
+// =================================================================================================
+// scratch arena: device memory a scene keeps per stream for the temporaries of its calls (staged host buffers, per-walk
+// totals, block statistics, counters).  Calls on one stream are ordered, so the next call may reuse the bytes of the
+// previous one; steady-state calls allocate nothing.  (Round 1 used cudaMallocAsync / cudaFreeAsync per call and raised
+// the release threshold of the device's DEFAULT memory pool -- a process-wide side effect, and ~10 driver calls per solve.)
+// =================================================================================================
+struct Arena {
+    struct Block { char* p; size_t cap, off; };
+    std::vector<Block> blocks;
+    void reset() {                                       // start of a call: everything is free again
+        if (blocks.size() > 1) {                         // the previous call outgrew its block: one block of the total size
+            size_t tot = 0;
+            for (auto& b : blocks) { tot += b.cap; cudaFree(b.p); }   // cudaFree waits for the device: nothing is in use
+            blocks.clear();
+            char* p = nullptr;
+            if (cudaMalloc((void**)&p, tot) == cudaSuccess) blocks.push_back({p, tot, 0}); else cudaGetLastError();
+        }
+        for (auto& b : blocks) b.off = 0;
+    }
+    void* take(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (!blocks.empty()) { Block& b = blocks.back(); if (b.off + bytes <= b.cap) { void* r = b.p + b.off; b.off += bytes; return r; } }
+        const size_t cap = std::max(bytes + (bytes >> 2), (size_t)1 << 20);
+        char* p = nullptr;
+        if (cudaMalloc((void**)&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        blocks.push_back({p, cap, bytes});
+        return p;
+    }
+    size_t bytes() const { size_t t = 0; for (auto& b : blocks) t += b.cap; return t; }
+    void release() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); }
+};
 
 // =================================================================================================
 // handles
@@ -47,6 +80,16 @@ struct wost_scene {
     float bvh_slack = 0.f;                             // ray/box slack (1e-4 of the scene scale)
     int neu_closed = 0;                                // first Neumann vertex == last
     float phys_nudge = 0.f;                            // 1e-5 of the scene scale
+    float4* dseg_as_neu = nullptr;                     // the Dirichlet polyline in the Neumann layout and vice versa, for the
+    float4* nseg_as_dir = nullptr;                     //   primitive entry points (intersect on `which = 0`, distance on `which = 1`)
+    mutable std::mutex arena_mu;
+    mutable std::map<cudaStream_t, Arena> arenas;      // per stream (a scene may be used from several streams at once)
+    Arena* arena_for(cudaStream_t st) const {
+        std::lock_guard<std::mutex> lk(arena_mu);
+        Arena& a = arenas[st];
+        a.reset();
+        return &a;
+    }
 };
 
 struct wost_field {
@@ -249,25 +292,27 @@ static bool is_device_ptr(const void* p) {
 template <typename T>
 struct Staged {
     T* dev = nullptr; T* host = nullptr; size_t count = 0; bool temp = false; bool is_out = false; cudaStream_t st = nullptr;
-    int init(const T* p, size_t n, bool out, cudaStream_t s) {
+    bool pooled = false;                                                // temporary from cudaMallocAsync (no arena given)
+    int init(const T* p, size_t n, bool out, cudaStream_t s, Arena* ar = nullptr) {
         count = n; is_out = out; st = s;
         if (!p || n == 0) { dev = nullptr; return 0; }
         if (is_device_ptr(p)) { dev = const_cast<T*>(p); return 0; }
         host = const_cast<T*>(p); temp = true;
-        CU(cudaMallocAsync((void**)&dev, n * sizeof(T), s));
+        if (ar) { dev = (T*)ar->take(n * sizeof(T)); if (!dev) return fail(WOST_ERR_ALLOC, "device scratch allocation failed"); }
+        else { CU(cudaMallocAsync((void**)&dev, n * sizeof(T), s)); pooled = true; }
         if (!out) CU(cudaMemcpyAsync(dev, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
         return 0;
     }
     int finish() {
         if (temp && dev) {
             if (is_out) CU(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
-            CU(cudaFreeAsync(dev, st));
+            if (pooled) CU(cudaFreeAsync(dev, st));
             dev = nullptr;
         }
         return 0;
     }
     bool host_out() const { return temp && is_out; }
-    ~Staged() { if (temp && dev) cudaFreeAsync(dev, st); }             // error paths: finish() was not reached
+    ~Staged() { if (pooled && dev) cudaFreeAsync(dev, st); }           // error paths: finish() was not reached
     Staged() = default;
     Staged(const Staged&) = delete;
     Staged& operator=(const Staged&) = delete;
@@ -276,10 +321,14 @@ struct Staged {
 // stream-ordered scratch buffer, released on every exit path
 template <typename T>
 struct Scratch {
-    T* p = nullptr; cudaStream_t st = nullptr;
-    int alloc(size_t n, cudaStream_t s) { st = s; CU(cudaMallocAsync((void**)&p, n * sizeof(T), s)); return 0; }
-    int release() { if (p) { T* q = p; p = nullptr; CU(cudaFreeAsync(q, st)); } return 0; }
-    ~Scratch() { if (p) cudaFreeAsync(p, st); }                         // error paths
+    T* p = nullptr; cudaStream_t st = nullptr; bool pooled = false;
+    int alloc(size_t n, cudaStream_t s, Arena* ar = nullptr) {
+        st = s;
+        if (ar) { p = (T*)ar->take(n * sizeof(T)); if (!p) return fail(WOST_ERR_ALLOC, "device scratch allocation failed"); return 0; }
+        CU(cudaMallocAsync((void**)&p, n * sizeof(T), s)); pooled = true; return 0;
+    }
+    int release() { if (p) { T* q = p; p = nullptr; if (pooled) CU(cudaFreeAsync(q, st)); } return 0; }
+    ~Scratch() { if (p && pooled) cudaFreeAsync(p, st); }               // error paths
     Scratch() = default;
     Scratch(const Scratch&) = delete;
     Scratch& operator=(const Scratch&) = delete;
@@ -290,18 +339,6 @@ struct DeviceGuard {
     explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true; }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-
-static std::once_flag g_pool_once[64];
-static void tune_pool(int device) {
-    if (device < 0 || device >= 64) return;
-    std::call_once(g_pool_once[device], [device] {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long thr = ~0ull;   // keep freed scratch cached: solves are called in a loop
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    });
-}
 
 // Implicit BVH over the index order of a polyline (see wost_device.cuh).  `xy` are the nvtx vertices.
 static std::vector<float4> build_bvh(const float* xy, int nvtx, float inflate, int* n_leaves_out) {
@@ -550,6 +587,20 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         ns[2 * k] = make_float4(ax, ay, ux, uy);
         ns[2 * k + 1] = make_float4(nx, ny, atan2f(ny, nx), 0.0f);       // solvers/WoStSolver.py:228
     }
+    // the other layout of each polyline, for the primitive entry points (PolyLinesSimple methods work on either boundary)
+    std::vector<float4> ds_n(ds.size()), ns_d(ns.size());
+    for (int k = 0; k + 1 < nd; ++k) {
+        const float ax = ds[2 * k].x, ay = ds[2 * k].y; volatile float ux = ds[2 * k + 1].x, uy = ds[2 * k + 1].y;
+        volatile float xx = ux * ux;
+        const float len = sqrtf(fmaf(uy, uy, xx));
+        volatile float tx = ux / len, ty = uy / len;
+        ds_n[2 * k] = make_float4(ax, ay, ux, uy); ds_n[2 * k + 1] = make_float4(-ty, tx, atan2f(tx, -ty), 0.0f);
+    }
+    for (int k = 0; k + 1 < nn; ++k) {
+        volatile float ax = ns[2 * k].x, ay = ns[2 * k].y, ux = ns[2 * k].z, uy = ns[2 * k].w;
+        volatile float xx = ux * ux, yy = uy * uy; volatile float uu = xx + yy;
+        ns_d[2 * k] = make_float4(ax, ay, nxy[2 * k + 2], nxy[2 * k + 3]); ns_d[2 * k + 1] = make_float4(ux, uy, uu, 0.0f);
+    }
     auto* s = new wost_scene();
     s->device = device; s->n_dvtx = nd; s->n_nvtx = nn; s->n_dseg = nd - 1; s->n_nseg = nn ? nn - 1 : 0;
     cudaDeviceProp prop{};
@@ -561,8 +612,14 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         e = cudaMalloc((void**)&s->nseg, ns.size() * sizeof(float4));
         if (e == cudaSuccess) e = cudaMemcpy(s->nseg, ns.data(), ns.size() * sizeof(float4), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->dseg_as_neu, ds_n.size() * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpy(s->dseg_as_neu, ds_n.data(), ds_n.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !ns_d.empty()) {
+        e = cudaMalloc((void**)&s->nseg_as_dir, ns_d.size() * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMemcpy(s->nseg_as_dir, ns_d.data(), ns_d.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
-        cudaFree(s->dseg); cudaFree(s->nseg); delete s;
+        cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dseg_as_neu); cudaFree(s->nseg_as_dir); delete s;
         return fail(WOST_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
     }
     if (nn > 0) {
@@ -621,7 +678,6 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
             return fail(WOST_ERR_CUDA, std::string("BVH upload: ") + cudaGetErrorString(be));
         }
     }
-    tune_pool(device);
     *out = s;
     return WOST_OK;
 }
@@ -631,7 +687,21 @@ int wost_scene_destroy(wost_scene_t* s) {
     DeviceGuard g(s->device);
     cudaFree(s->dseg); cudaFree(s->nseg); cudaFree(s->dbvh); cudaFree(s->nbvh); cudaFree(s->ncones);
     cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones); cudaFree(s->dwide_boxes);
+    cudaFree(s->dseg_as_neu); cudaFree(s->nseg_as_dir);
+    for (auto& kv : s->arenas) kv.second.release();
     delete s;
+    return WOST_OK;
+}
+
+int wost_scene_trim(wost_scene_t* s, int64_t* out_released_bytes) {
+    if (!s) return fail(WOST_ERR_INVALID, "scene is NULL");
+    DeviceGuard g(s->device);
+    std::lock_guard<std::mutex> lk(s->arena_mu);
+    size_t tot = 0;
+    CU(cudaDeviceSynchronize());                                         // nothing may still be using the scratch
+    for (auto& kv : s->arenas) { tot += kv.second.bytes(); kv.second.release(); }
+    s->arenas.clear();
+    if (out_released_bytes) *out_released_bytes = (int64_t)tot;
     return WOST_OK;
 }
 
@@ -784,6 +854,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     DeviceGuard g(scene->device);
     if (!g.ok) return fail(WOST_ERR_CUDA, "cannot select the scene's device");
     cudaStream_t st = (cudaStream_t)stream;
+    Arena* ar = scene->arena_for(st);                                  // this call's temporaries (reused by the next call on `st`)
     const long long W = P->n_walks;
     const long long nblk = (W + WOST_WALK_BLOCK - 1) / WOST_WALK_BLOCK;
     const bool trace = n_trace > 0;
@@ -795,20 +866,20 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
 
     Staged<float> s_pts, s_trace, s_icdf, s_maj; Staged<double> s_mean, s_m2, s_blk; Staged<uint64_t> s_steps; Staged<int32_t> s_tlen;
     int rc;
-    if ((rc = s_pts.init(pts_xy, 2 * n_pts, false, st))) return rc;
+    if ((rc = s_pts.init(pts_xy, 2 * n_pts, false, st, ar))) return rc;
     const bool use_icdf = delta && !phys_delta;
-    if ((rc = s_icdf.init(use_icdf ? P->screened_icdf : nullptr, use_icdf ? P->icdf_len : 0, false, st))) return rc;
+    if ((rc = s_icdf.init(use_icdf ? P->screened_icdf : nullptr, use_icdf ? P->icdf_len : 0, false, st, ar))) return rc;
     size_t maj_len = 0;
     if (phys_delta && P->majorant_levels > 0) {
         if (P->majorant_levels > 13 || !P->majorant || !(P->majorant_dx > 0.0f) || !(P->majorant_dy > 0.0f))
             return fail(WOST_ERR_INVALID, "majorant pyramid: 1..13 levels, data and positive cell sizes needed");
         for (int l = 0, n = 1 << (P->majorant_levels - 1); l < P->majorant_levels; ++l, n >>= 1) maj_len += (size_t)n * n;
     }
-    if ((rc = s_maj.init(maj_len ? P->majorant : nullptr, maj_len, false, st))) return rc;
-    if ((rc = s_mean.init(out_mean, (size_t)S * n_pts, true, st)) || (rc = s_m2.init(out_m2, (size_t)S * n_pts, true, st)) ||
-        (rc = s_blk.init(out_block_stats, (size_t)S * 2 * n_pts * nblk, true, st)) || (rc = s_steps.init(out_steps, 1, true, st)) ||
-        (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * (trace_cap + 1) * 8 : 0, true, st)) ||
-        (rc = s_tlen.init(out_trace_len, trace ? n_trace : 0, true, st))) return rc;
+    if ((rc = s_maj.init(maj_len ? P->majorant : nullptr, maj_len, false, st, ar))) return rc;
+    if ((rc = s_mean.init(out_mean, (size_t)S * n_pts, true, st, ar)) || (rc = s_m2.init(out_m2, (size_t)S * n_pts, true, st, ar)) ||
+        (rc = s_blk.init(out_block_stats, (size_t)S * 2 * n_pts * nblk, true, st, ar)) || (rc = s_steps.init(out_steps, 1, true, st, ar)) ||
+        (rc = s_trace.init(out_trace, trace ? (size_t)n_trace * (trace_cap + 1) * 8 : 0, true, st, ar)) ||
+        (rc = s_tlen.init(out_trace_len, trace ? n_trace : 0, true, st, ar))) return rc;
 
     // scratch: per-walk totals (unless the caller wants them), counters, block statistics
     // The per-walk buffer is bounded: evaluation points are processed in passes of at most WOST_MAX_WALK_VALS walks
@@ -820,7 +891,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     Scratch<float> vals_s, alpha0_s; Scratch<DevField> srcs_s; Scratch<float4> sup_s; Scratch<unsigned long long> ctrs_s; Scratch<double> blk_s;
     float* vals = nullptr; bool vals_temp = false;
     const bool vals_dev_out = out_walk_vals && is_device_ptr(out_walk_vals);
-    if (!vals_dev_out) { if ((rc = vals_s.alloc((size_t)pts_per_pass * W * S, st))) return rc; vals = vals_s.p; vals_temp = true; }
+    if (!vals_dev_out) { if ((rc = vals_s.alloc((size_t)pts_per_pass * W * S, st, ar))) return rc; vals = vals_s.p; vals_temp = true; }
     // shared-memory layout of the walk kernel (float4 units): field headers | staged segment tables | term tables
     const size_t d_bytes = scene->dbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_dseg;
     const size_t n_bytes = scene->nbvh ? 0 : sizeof(float4) * 2 * (size_t)scene->n_nseg;
@@ -838,19 +909,19 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (smem + 16 * 1024 > scene->smem_optin)
         return fail(WOST_ERR_UNSUPPORTED, "field term tables and segment tables do not fit shared memory (" + std::to_string(smem) + " bytes)");
     if (n_sources > 0) {
-        if ((rc = srcs_s.alloc(n_sources, st)) || (rc = sup_s.alloc(n_sources, st))) return rc;
+        if ((rc = srcs_s.alloc(n_sources, st, ar)) || (rc = sup_s.alloc(n_sources, st, ar))) return rc;
         d_srcs = srcs_s.p; d_sup = sup_s.p;
         CU(cudaMemcpyAsync(d_srcs, h.data(), sizeof(DevField) * n_sources, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_sup, hs.data(), sizeof(float4) * n_sources, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));                                   // the host vectors go out of scope
     }
-    if ((rc = ctrs_s.alloc(2, st))) return rc;
+    if ((rc = ctrs_s.alloc(2, st, ar))) return rc;
     unsigned long long* ctrs = ctrs_s.p;
-    if (delta && (rc = alpha0_s.alloc((size_t)n_pts, st))) return rc;
+    if (delta && (rc = alpha0_s.alloc((size_t)n_pts, st, ar))) return rc;
     float* alpha0 = alpha0_s.p;
     CU(cudaMemsetAsync(ctrs, 0, 2 * sizeof(unsigned long long), st));
     double* blk = s_blk.dev; bool blk_temp = false;
-    if (!blk) { if ((rc = blk_s.alloc((size_t)2 * n_pts * nblk * S, st))) return rc; blk = blk_s.p; blk_temp = true; }
+    if (!blk) { if ((rc = blk_s.alloc((size_t)2 * n_pts * nblk * S, st, ar))) return rc; blk = blk_s.p; blk_temp = true; }
     if (trace) {
         CU(cudaMemsetAsync(s_trace.dev, 0xff, sizeof(float) * (size_t)n_trace * (trace_cap + 1) * 8, st));   // NaN fill
         CU(cudaMemsetAsync(s_tlen.dev, 0, sizeof(int32_t) * n_trace, st));
@@ -1023,32 +1094,16 @@ int wost_geom_distance(const wost_scene_t* s, int32_t which, const float* p, int
     if (B == 0) return WOST_OK;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // the distance kernel wants the Dirichlet layout; build it on the fly for the Neumann polyline
-    float4* tmp = nullptr;
-    const float4* seg = v.seg;
-    if (!v.dirichlet_layout) {
-        std::vector<float4> h(2 * (size_t)v.n), d(2 * (size_t)v.n);
-        CU(cudaMemcpy(h.data(), v.seg, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < v.n; ++k) {
-            volatile float ax = h[2 * k].x, ay = h[2 * k].y, ux = h[2 * k].z, uy = h[2 * k].w;
-            volatile float xx = ux * ux, yy = uy * uy; volatile float uu = xx + yy;
-            // b is the next segment's a (or a + u for the last one: exact for polylines built from vertices)
-            float bx = (k + 1 < v.n) ? h[2 * k + 2].x : ax + ux, by = (k + 1 < v.n) ? h[2 * k + 2].y : ay + uy;
-            d[2 * k] = make_float4(ax, ay, bx, by); d[2 * k + 1] = make_float4(ux, uy, uu, 0.0f);
-        }
-        CU(cudaMallocAsync((void**)&tmp, sizeof(float4) * d.size(), st));
-        CU(cudaMemcpyAsync(tmp, d.data(), sizeof(float4) * d.size(), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));
-        seg = tmp;
-    }
+    Arena* ar = s->arena_for(st);
+    // the distance kernel wants the Dirichlet layout: the Neumann polyline has one too, built by wost_scene_create
+    const float4* seg = v.dirichlet_layout ? v.seg : s->nseg_as_dir;
     Staged<float> sp, sd; Staged<int32_t> ss;
-    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sd.init(out_d, B, true, st)) || (rc = ss.init(out_seg, B, true, st))) return rc;
+    if ((rc = sp.init(p, 2 * B, false, st, ar)) || (rc = sd.init(out_d, B, true, st, ar)) || (rc = ss.init(out_seg, B, true, st, ar))) return rc;
     Bvh bvh{}; if (v.dirichlet_layout) { bvh.nodes = s->dbvh; bvh.n_leaves = s->dbvh_leaves; }
     geom_distance_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, bvh, sp.dev, B, sd.dev, ss.dev);
     CU(cudaGetLastError());
     const bool sync = sd.host_out() || ss.host_out();
     if ((rc = sp.finish()) || (rc = sd.finish()) || (rc = ss.finish())) return rc;
-    if (tmp) CU(cudaFreeAsync(tmp, st));
     if (sync) CU(cudaStreamSynchronize(st));
     return WOST_OK;
 }
@@ -1060,8 +1115,9 @@ int wost_geom_silhouette(const wost_scene_t* s, int32_t which, const float* p, i
     if (B == 0) return WOST_OK;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
+    Arena* ar = s->arena_for(st);
     Staged<float> sp, sd; Staged<uint8_t> sm;
-    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sd.init(out_d, B, true, st)) || (rc = sm.init(out_mask, (size_t)B * (v.n - 1), true, st))) return rc;
+    if ((rc = sp.init(p, 2 * B, false, st, ar)) || (rc = sd.init(out_d, B, true, st, ar)) || (rc = sm.init(out_mask, (size_t)B * (v.n - 1), true, st, ar))) return rc;
     Bvh bvh{}; if (!v.dirichlet_layout) { bvh.nodes = s->nbvh; bvh.cones = s->ncones; bvh.n_leaves = s->nbvh_leaves; }
     geom_silhouette_kernel<<<blocks_for(B, 256), 256, 0, st>>>(v, bvh, sp.dev, B, sd.dev, sm.dev);
     CU(cudaGetLastError());
@@ -1078,8 +1134,9 @@ int wost_geom_ray(const wost_scene_t* s, int32_t which, const float* p, const fl
     if (B == 0) return WOST_OK;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
+    Arena* ar = s->arena_for(st);
     Staged<float> sp, sdir, so;
-    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sdir.init(dir, 2 * B, false, st)) || (rc = so.init(out_s, (size_t)B * v.n, true, st))) return rc;
+    if ((rc = sp.init(p, 2 * B, false, st, ar)) || (rc = sdir.init(dir, 2 * B, false, st, ar)) || (rc = so.init(out_s, (size_t)B * v.n, true, st, ar))) return rc;
     geom_ray_kernel<<<blocks_for(B, 256), 256, 0, st>>>(v, sp.dev, sdir.dev, B, so.dev);
     CU(cudaGetLastError());
     const bool sync = so.host_out();
@@ -1096,33 +1153,18 @@ int wost_geom_intersect(const wost_scene_t* s, int32_t which, const float* p, co
     if (B == 0) return WOST_OK;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // intersect runs on the Neumann layout; convert a Dirichlet polyline on the fly
-    float4* tmp = nullptr; const float4* seg = v.seg;
-    if (v.dirichlet_layout) {
-        std::vector<float4> h(2 * (size_t)v.n), d(2 * (size_t)v.n);
-        CU(cudaMemcpy(h.data(), v.seg, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < v.n; ++k) {
-            const float ax = h[2 * k].x, ay = h[2 * k].y; volatile float ux = h[2 * k + 1].x, uy = h[2 * k + 1].y;
-            volatile float xx = ux * ux;
-            const float len = sqrtf(fmaf(uy, uy, xx));
-            volatile float tx = ux / len, ty = uy / len;
-            d[2 * k] = make_float4(ax, ay, ux, uy); d[2 * k + 1] = make_float4(-ty, tx, atan2f(tx, -ty), 0.0f);
-        }
-        CU(cudaMallocAsync((void**)&tmp, sizeof(float4) * d.size(), st));
-        CU(cudaMemcpyAsync(tmp, d.data(), sizeof(float4) * d.size(), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));
-        seg = tmp;
-    }
+    Arena* ar = s->arena_for(st);
+    // intersect runs on the Neumann layout: the Dirichlet polyline has one too, built by wost_scene_create
+    const float4* seg = v.dirichlet_layout ? s->dseg_as_neu : v.seg;
     Staged<float> sp, sdir, sr, spt, snr; Staged<uint8_t> sf; Staged<int32_t> ss;
-    if ((rc = sp.init(p, 2 * B, false, st)) || (rc = sdir.init(dir, 2 * B, false, st)) || (rc = sr.init(r, B, false, st)) ||
-        (rc = spt.init(out_pt, 2 * B, true, st)) || (rc = snr.init(out_nrm, 2 * B, true, st)) || (rc = sf.init(out_found, B, true, st)) ||
-        (rc = ss.init(out_seg, B, true, st))) return rc;
+    if ((rc = sp.init(p, 2 * B, false, st, ar)) || (rc = sdir.init(dir, 2 * B, false, st, ar)) || (rc = sr.init(r, B, false, st, ar)) ||
+        (rc = spt.init(out_pt, 2 * B, true, st, ar)) || (rc = snr.init(out_nrm, 2 * B, true, st, ar)) || (rc = sf.init(out_found, B, true, st, ar)) ||
+        (rc = ss.init(out_seg, B, true, st, ar))) return rc;
     Bvh bvh{}; if (!v.dirichlet_layout) { bvh.nodes = s->nbvh; bvh.n_leaves = s->nbvh_leaves; }
     geom_intersect_kernel<<<blocks_for(B, 256), 256, 0, st>>>(seg, v.n, bvh, s->bvh_slack, sp.dev, sdir.dev, sr.dev, B, spt.dev, snr.dev, sf.dev, ss.dev);
     CU(cudaGetLastError());
     const bool sync = spt.host_out() || snr.host_out() || sf.host_out() || ss.host_out();
     if ((rc = sp.finish()) || (rc = sdir.finish()) || (rc = sr.finish()) || (rc = spt.finish()) || (rc = snr.finish()) || (rc = sf.finish()) || (rc = ss.finish())) return rc;
-    if (tmp) CU(cudaFreeAsync(tmp, st));
     if (sync) CU(cudaStreamSynchronize(st));
     return WOST_OK;
 }

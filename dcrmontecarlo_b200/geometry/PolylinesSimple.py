@@ -33,13 +33,24 @@ class PolyLinesSimple(PolyLines):
         super().__init__(points)
         self._scene = None
         self._scene_key = None
+        self._scene_src = None
 
     # the scene holds the polyline in both the Dirichlet and the Neumann slot so every query is available
     def _scene_for(self):
-        pts = nat.host_f32(self.points).reshape(-1, 2)
-        key = (pts.tobytes(), nat.current_device())
+        """O(1) per query: the scene is rebuilt only when ``points`` is another tensor or was modified in place (torch
+        bumps a tensor's version counter on every in-place write) -- not by comparing the vertex data on every call."""
+        p = self.points
+        dev = nat.current_device()
+        if isinstance(p, torch.Tensor):
+            key = (p._version, dev)
+            if self._scene is None or self._scene_src is not p or self._scene_key != key:
+                pts = nat.host_f32(p).reshape(-1, 2)
+                self._scene, self._scene_src, self._scene_key = nat.Scene(pts, pts), p, key
+            return self._scene
+        pts = nat.host_f32(p).reshape(-1, 2)                           # not a tensor (assigned by hand): compare the data
+        key = (pts.tobytes(), dev)
         if self._scene is None or self._scene_key != key:
-            self._scene, self._scene_key = nat.Scene(pts, pts), key
+            self._scene, self._scene_src, self._scene_key = nat.Scene(pts, pts), None, key
         return self._scene
 
     @staticmethod

@@ -331,12 +331,17 @@ class WostSolver_2D:
         return self._cache[key][1]
 
     def _scene(self, device):
-        d = nat.host_f32(self.dirichletBoundary.points)
-        n = None if self.neumannBoundary is None else nat.host_f32(self.neumannBoundary.points)
-        key = ("scene", d.tobytes(), None if n is None else n.tobytes(), device)
-        if key not in self._cache:
-            self._cache[key] = nat.Scene(d, n, device)
-        return self._cache[key]
+        # one scene per device, rebuilt when a boundary's `points` is another tensor or was written in place (version counter)
+        dp = self.dirichletBoundary.points
+        npts = None if self.neumannBoundary is None else self.neumannBoundary.points
+        tok = tuple((id(p), getattr(p, "_version", None)) if isinstance(p, torch.Tensor) else (None if p is None else nat.host_f32(p).tobytes())
+                    for p in (dp, npts))
+        key = ("scene", device)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != tok:
+            hit = (tok, nat.Scene(nat.host_f32(dp), None if npts is None else nat.host_f32(npts), device), (dp, npts))   # refs keep the ids unique
+            self._cache[key] = hit
+        return hit[1]
 
     def _device_problem(self, device):
         """Scene handle, wost_fields_t and delta-tracking parameters for one device."""

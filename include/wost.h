@@ -150,6 +150,9 @@ int wost_scene_create(const float* dirichlet_xy, int32_t n_dirichlet_vtx,
                       const float* neumann_xy, int32_t n_neumann_vtx,
                       int32_t device, wost_scene_t** out);
 int wost_scene_destroy(wost_scene_t* scene);
+/* A scene keeps the device scratch of its calls (per stream: staged host buffers, per-walk totals, statistics) so that
+ * steady-state calls allocate nothing; this returns that memory to the driver (waits for the device first). */
+int wost_scene_trim(wost_scene_t* scene, int64_t* out_released_bytes);
 
 int wost_field_create(const wost_field_desc_t* desc, int32_t device, wost_field_t** out);
 int wost_field_destroy(wost_field_t* field);
