@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -99,7 +100,9 @@ struct wost_field {
     wost_term_t* terms = nullptr;
     float* grid = nullptr;
     std::vector<wost_term_t> h_terms;     // host copy of the device-form terms (code generation for the specialised kernels)
+    uint64_t uid = 0;                     // unique per created field (fields are immutable): cache key of specialised kernels
 };
+static std::atomic<uint64_t> g_field_uid{1};
 
 // =================================================================================================
 // kernels: the walk (body in wost_walk.cuh; these are the statically compiled instantiations, fields by interpreter)
@@ -724,7 +727,7 @@ int wost_field_create(const wost_field_desc_t* d, int32_t device, wost_field_t**
     DeviceGuard g(device);
     if (!g.ok) return fail(WOST_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
     auto* f = new wost_field();
-    f->device = device;
+    f->device = device; f->uid = g_field_uid.fetch_add(1);
     DevField& D = f->d;
     D.present = 1; D.kind = d->kind; D.n_terms = d->kind == WOST_FIELD_TERMS ? d->n_terms : 0; D.mask_kind = d->mask_kind;
     D.c0 = d->c0; D.m0 = d->mask[0]; D.m1 = d->mask[1]; D.m2 = d->mask[2]; D.m3 = d->mask[3]; D.outside = d->outside;
@@ -961,8 +964,8 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     auto t_now = [] { return std::chrono::steady_clock::now(); };
     auto t_ms = [](std::chrono::steady_clock::time_point a_, std::chrono::steady_clock::time_point b_) { return std::chrono::duration<double, std::milli>(b_ - a_).count(); };
     const auto T0 = t_now();
-    {   // per-solver specialised kernel (wost_jit.inc): params->jit 0 = auto (jobs of >= 2^18 walks, or already compiled),
-        // 1 = always, 2 = never; the environment variable WOST_JIT (0 / 1) overrides
+    {   // per-solver specialised kernel (wost_jit.inc): params->jit 0 = auto (jobs of >= 2^18 walks, the 8th solve with the
+        // same fields, or already compiled), 1 = always, 2 = never; the environment variable WOST_JIT (0 / 1) overrides
         int mode = P->jit;
         if (const char* e = std::getenv("WOST_JIT")) mode = std::atoi(e) ? 1 : 2;
         std::string why = "specialisation switched off";
@@ -974,7 +977,8 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
                 fl.n_dseg = scene->n_dseg; fl.n_nseg = scene->n_nseg; fl.sil_coop_max = a.sil_coop_max; fl.ray_coop_max = a.ray_coop_max;
             }
             wost_fields_t none{};
-            K = jit::get(fields ? fields : &none, fl, scene->device, mode == 1 || (long long)n_pts * W >= (1ll << 18), &why);
+            K = jit::get(fields ? fields : &none, fl, scene->device, mode == 1 || (long long)n_pts * W >= (1ll << 18),
+                         env_int("WOST_JIT_AUTO_AFTER", 8), &why);
         }
         if (K) { kern = (const void*)K->fn; why.clear(); }
         else if (mode == 1 && !std::getenv("WOST_JIT_SOFT"))

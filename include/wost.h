@@ -129,7 +129,7 @@ typedef struct {
     float majorant_x0, majorant_y0, majorant_dx, majorant_dy;
     /* Per-solver specialised kernel: the fields of this solve compiled into the walk kernel with NVRTC (cached per field
      * set), instead of the interpreter over field descriptors.  Results are bit-identical either way.
-     * 0 = auto (jobs of >= 2^18 walks, or whenever the kernel is compiled already), 1 = always (error if NVRTC is
+     * 0 = auto (jobs of >= 2^18 walks, the 8th solve with the same fields, or whenever the kernel is compiled already), 1 = always (error if NVRTC is
      * unavailable), 2 = never.  The environment variable WOST_JIT (0 / 1) overrides; WOST_JIT_CACHE=<dir> keeps compiled
      * kernels on disk. */
     int32_t jit;
