@@ -224,9 +224,12 @@ def _set_majorant(prm, majorant):
 def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: float, *, delta: bool = False,
           sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0, point_index_base: int = 0,
           walk_offset: int = 0, want_block_stats: bool = False, want_walk_vals: bool = False, n_trace: int = 0,
-          trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference", majorant=None, jit: str = "auto"):
+          trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference", majorant=None, jit: str = "auto",
+          out: dict | None = None):
     """One wost_solve call.  ``pts`` may be a host array/tensor or a CUDA tensor on the scene's device.
-    With ``device_outputs`` the results stay on the device as torch tensors (stream-ordered, no sync)."""
+    With ``device_outputs`` the results stay on the device as torch tensors (stream-ordered, no sync); ``out`` may then
+    hold preallocated contiguous CUDA tensors ``mean`` / ``m2`` (P,) float64, ``steps`` (1,) int64, ``block_stats``
+    (P, nblk, 2) float64 to write into (e.g. slices of a gather buffer)."""
     dev = scene.device
     if isinstance(pts, torch.Tensor) and pts.is_cuda:
         p = pts.detach().to(torch.float32).contiguous().reshape(-1, 2)
@@ -249,10 +252,14 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
     if device_outputs:
         tdev = torch.device("cuda", dev)
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=tdev)
-        mean, m2 = mk((P,), torch.float64), mk((P,), torch.float64)
-        blk = mk((P, nblk, 2), torch.float64) if want_block_stats else None
+        o = out or {}
+        mean = o["mean"] if "mean" in o else mk((P,), torch.float64)
+        m2 = o["m2"] if "m2" in o else mk((P,), torch.float64)
+        blk = (o["block_stats"] if "block_stats" in o else mk((P, nblk, 2), torch.float64)) if want_block_stats else None
         vals = mk((P, n_walks), torch.float32) if want_walk_vals else None
-        steps = mk((1,), torch.int64)
+        steps = o["steps"] if "steps" in o else mk((1,), torch.int64)
+        for t, n in ((mean, P), (m2, P), (steps, 1)) + (((blk, P * nblk * 2),) if blk is not None else ()):
+            assert t.is_cuda and t.is_contiguous() and t.numel() == n and t.element_size() == 8, "preallocated outputs: contiguous 8-byte CUDA tensors"
         trace = mk((n_trace, trace_cap + 1, 8), torch.float32) if n_trace else None
         tlen = mk((n_trace,), torch.int32) if n_trace else None
     else:

@@ -380,7 +380,7 @@ class WostSolver_2D:
     # ------------------------------------------------------------------------------------------------
     def solve_raw(self, solvePoints, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None, point_index_base=0,
                   walk_offset=0, want_block_stats=False, want_walk_vals=False, n_trace=0, trace_cap=0,
-                  device_outputs=False, device=None, jit=None):
+                  device_outputs=False, device=None, jit=None, out=None):
         """One kernel pass over ``solvePoints`` on one device; returns the raw statistics dict
         (mean, m2, steps, optional block_stats / walk_vals / trace).  Building block of :meth:`solve`
         and of the multi-GPU driver (:mod:`dcrmontecarlo_b200.distributed`)."""
@@ -394,12 +394,13 @@ class WostSolver_2D:
                         sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
                         point_index_base=point_index_base, walk_offset=walk_offset, want_block_stats=want_block_stats,
                         want_walk_vals=want_walk_vals, n_trace=n_trace, trace_cap=trace_cap, device_outputs=device_outputs,
-                        compat=self.compat, majorant=self._device_majorant(device), jit=jit or self.jit)
+                        compat=self.compat, majorant=self._device_majorant(device), jit=jit or self.jit, out=out)
         res["seed"] = seed
         return res
 
     def solve_multi_source(self, solvePoints, sources, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None,
-                           want_block_stats=False, device_outputs=False, device=None, jit=None):
+                           want_block_stats=False, device_outputs=False, device=None, jit=None, point_index_base=0,
+                           walk_offset=0):
         """Shared-walk solve for many source terms (not in the reference, which re-walks per source): the walk does not
         depend on ``f``, so one set of walks gives the estimate for every source in ``sources`` (callables or fields).
         Returns ``mean`` / ``m2`` of shape ``(len(sources), P)``; row ``s`` equals what :meth:`solve_raw` returns with
@@ -413,6 +414,7 @@ class WostSolver_2D:
         res = nat.solve_multi_source(scene, fields, devs, solvePoints, int(nWalks), int(maxSteps), float(eps),
                                      delta=self.use_delta_tracking, sp_mode=self.sp_mode,
                                      sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
+                                     point_index_base=point_index_base, walk_offset=walk_offset,
                                      want_block_stats=want_block_stats, device_outputs=device_outputs, compat=self.compat,
                                      majorant=self._device_majorant(device), jit=jit or self.jit)
         res["seed"] = seed

@@ -71,8 +71,9 @@ class DCRSurvey:
             shared_walks: bool = False) -> dict:
         """Potentials at every electrode for every source.  Returns
         ``potentials`` (S, E) float64, ``stderr`` (S, E), ``dV`` (S, R) = V_M - V_N per receiver dipole, ``steps``.
-        With an initialised ``torch.distributed`` group the sources are dealt round-robin to the ranks and the
-        result is gathered on every rank; the same ``seed`` gives the same numbers for any number of ranks.
+        With an initialised ``torch.distributed`` group the work is sharded over the ranks -- the sources round-robin, or
+        with ``shared_walks`` the electrodes -- and the result is gathered on every rank; the same ``seed`` gives the same
+        numbers for any number of ranks.
 
         ``shared_walks=True``: the walk does not depend on the source term, so ONE set of walks per electrode serves
         all sources (``wost_solve_multi_source``) — the cost of a survey becomes almost independent of the number of
@@ -81,26 +82,23 @@ class DCRSurvey:
         import torch.distributed as dist
 
         world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
+        on_nccl = world > 1 and dist.get_backend() == "nccl"
         if seed is None:
             hi, lo = torch.randint(0, 1 << 31, (2,), dtype=torch.int64).tolist()
             seed = (hi << 31) | lo
-        if world > 1:                                                     # one key for the whole job
-            t = torch.tensor([seed if rank == 0 else 0], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
-            dist.broadcast(t, src=0)
-            seed = int(t.item())
+            if world > 1:                                                 # one key for the whole job
+                t = torch.tensor([seed if rank == 0 else 0], dtype=torch.int64, device="cuda" if on_nccl else "cpu")
+                dist.broadcast(t, src=0)
+                seed = int(t.item())
         S, E = len(self.sources), self.electrodes.shape[0]
+        if shared_walks:
+            return self._run_shared(nWalks, maxSteps, eps, seed, world, rank, on_nccl)
         pot, m2 = np.zeros((S, E)), np.zeros((S, E))
         steps = 0
         # One kernel launch per source over all electrodes.  A launch of a few electrodes does not fill the GPU (the
         # persistent grid is sized to the work), so sources are issued round-robin on several streams with
         # device-resident results and collected once at the end.
         mine = list(range(rank, S, world))
-        if shared_walks and mine:
-            r = self.solver.solve_multi_source(self.electrodes, [self._fields[s] for s in mine], nWalks, maxSteps, eps, seed=seed)
-            for k, s in enumerate(mine):
-                pot[s], m2[s] = r["mean"][k], r["m2"][k]
-            steps += int(r["steps"][0])
-            mine = []
         n_streams = max(1, min(int(streams), len(mine)))
         if n_streams > 1:
             # streams are kept: torch's caching allocator pools memory per stream, fresh streams would re-allocate
@@ -126,12 +124,48 @@ class DCRSurvey:
             pot[s], m2[s] = r["mean"].cpu().numpy(), r["m2"].cpu().numpy()
             steps += int(r["steps"][0])
         if world > 1:
-            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            dev = "cuda" if on_nccl else "cpu"
             buf = torch.from_numpy(np.stack([pot, m2])).to(dev)
             dist.all_reduce(buf)                                          # disjoint rows: the sum is a gather
             st = torch.tensor([steps], dtype=torch.int64, device=dev)
             dist.all_reduce(st)
             pot, m2, steps = buf[0].cpu().numpy(), buf[1].cpu().numpy(), int(st.item())
+        return self._finish(pot, m2, steps, seed, nWalks)
+
+    def _run_shared(self, nWalks, maxSteps, eps, seed, world, rank, on_nccl):
+        """Shared walks: ONE set of walks per electrode serves every source, so the ELECTRODES are what is sharded over
+        the ranks (each rank: its slice of the electrode line x all sources x all walks, one launch), and one
+        all-gather of the (source, electrode) statistics leaves the full result on every rank.  Philox counters carry the
+        global electrode index, so the numbers do not depend on the number of ranks."""
+        import torch.distributed as dist
+
+        from .distributed import _split
+
+        S, E = len(self.sources), self.electrodes.shape[0]
+        edges = _split(E, world)
+        e0, e1 = edges[rank], edges[rank + 1]
+        emax = max(edges[r + 1] - edges[r] for r in range(world))
+        use_cuda = torch.cuda.is_available() and hasattr(self.solver, "_device_problem")
+        dev = torch.device("cuda", torch.cuda.current_device()) if (on_nccl or (world == 1 and use_cuda)) else torch.device("cpu")
+        send = torch.zeros(2 * S * emax + 1, dtype=torch.float64, device=dev)
+        if e1 > e0:
+            r = self.solver.solve_multi_source(self.electrodes[e0:e1], self._fields, nWalks, maxSteps, eps, seed=seed,
+                                               point_index_base=e0, device_outputs=dev.type == "cuda")
+            as_t = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dev)   # noqa: E731
+            blk = send[: 2 * S * emax].view(2, S, emax)
+            blk[0, :, : e1 - e0], blk[1, :, : e1 - e0] = as_t(r["mean"]), as_t(r["m2"])
+            send[2 * S * emax] = as_t(r["steps"]).reshape(-1)[0].to(torch.float64)
+        if world > 1:
+            recv = torch.empty(world, 2 * S * emax + 1, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(recv.view(-1), send, group=None)
+        else:
+            recv = send.view(1, -1)
+        parts = [recv[q, : 2 * S * emax].view(2, S, emax)[:, :, : edges[q + 1] - edges[q]] for q in range(world)]
+        full = torch.cat(parts, dim=2).cpu().numpy()                       # (2, S, E): the one host read of the run
+        steps = int(recv[:, 2 * S * emax].sum().item())
+        return self._finish(full[0], full[1], steps, seed, nWalks)
+
+    def _finish(self, pot, m2, steps, seed, nWalks):
         n = float(nWalks)
         stderr = np.sqrt(m2 / max(n - 1.0, 1.0) / n)
         M = np.array([r[0] for r in self.receivers]); N = np.array([r[1] for r in self.receivers])

@@ -93,6 +93,54 @@ def test_shard_plan_covers_everything_once():
             seen[sh.p0:sh.p1, sh.w0:sh.w1] += 1
             assert sh.n_walks == 0 or sh.w0 % WALK_BLOCK == 0          # walk shards start on reduction-block boundaries
         assert np.all(seen == 1)
-        if P >= world:
-            assert all(sh.w0 == 0 and sh.w1 == W for sh in plan)
+        by_points = all(sh.w0 == 0 and sh.w1 == W for sh in plan)
+        if by_points:
             assert max(sh.n_points for sh in plan) - min(sh.n_points for sh in plan) <= 1
+        # 'auto' balances: the busiest rank carries at most ~6 % more than its share whenever the shape allows it
+        work = [sh.n_points * sh.n_walks for sh in plan]
+        if P % world == 0 or P >= 16 * world or ((W + WALK_BLOCK - 1) // WALK_BLOCK) % world == 0:
+            assert max(work) <= 1.07 * (P * W / world) + WALK_BLOCK * P, (P, W, world, work)
+    assert all(sh.w0 == 0 and sh.w1 == 150 for sh in shard_plan(404, 150, 8))          # many points: by points
+    assert not all(sh.w1 == 4096 for sh in shard_plan(3, 4096, 2))                     # 3 points on 2 ranks: by walks (2 blocks each)
+
+
+# ---- DCRSurvey.run: electrode sharding (shared walks) and source sharding over ranks ---------------------------------
+class FakeSurveySolver:
+    """Stand-in for WostSolver_2D inside DCRSurvey: values depend on GLOBAL (source, electrode) indices only."""
+
+    def solve_multi_source(self, pts, sources, nWalks, maxSteps, eps, *, seed, point_index_base=0, device_outputs=False):
+        S, E = len(sources), len(pts)
+        mean = np.array([[np.float64(walk_value(point_index_base + e, s, seed)) for e in range(E)] for s in range(S)])
+        return dict(mean=mean, m2=np.abs(mean) * 3.0, steps=np.array([S * E * nWalks], np.uint64))
+
+
+def _survey_worker(rank, world, port, E, S, ret):
+    from dcrmontecarlo_b200 import scenarios as sc
+    from dcrmontecarlo_b200.survey import DCRSurvey, DipoleSource
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = sc.cfg5(9)
+    xs = torch.linspace(-40.0, 40.0, E)
+    survey = DCRSurvey.__new__(DCRSurvey)                              # no GPU here: assemble the object around the fake solver
+    survey.electrodes = torch.stack([xs, torch.zeros_like(xs)], dim=1)
+    survey.sources = [DipoleSource((-30.0 + k, 0.0), (30.0 - k, 0.0)) for k in range(S)]
+    survey.receivers = [(i, i + 1) for i in range(E - 1)]
+    survey.sink_sign, survey.solver, survey._streams = -1.0, FakeSurveySolver(), []
+    survey._fields = [src.field(-1.0) for src in survey.sources]
+    out = survey.run(nWalks=10, seed=5, shared_walks=True)
+    if rank == world - 1:
+        ret["pot"], ret["steps"] = out["potentials"].copy(), out["steps"]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,E,S", [(2, 9, 3), (3, 7, 2), (2, 1, 2)])
+def test_survey_electrode_sharding_is_independent_of_rank_count(world, E, S):
+    one = {}
+    _survey_worker(0, 1, 0, E, S, one)
+    ret = mp.Manager().dict()
+    mp.spawn(_survey_worker, args=(world, _free_port(), E, S, ret), nprocs=world, join=True)
+    assert np.array_equal(ret["pot"], one["pot"]) and ret["steps"] == one["steps"]

@@ -22,8 +22,11 @@ rep, kernel = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 
 with tempfile.TemporaryDirectory() as td:
-    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("WOST_LIB", str(ROOT / "dcrmontecarlo_b200" / "libwost.so"))], cwd=td, check=True, capture_output=True)
-    cubin = next(Path(td).glob("*.cubin"))
+    if os.environ.get("WOST_CUBIN"):                    # a specialised (NVRTC) kernel kept by WOST_JIT_CACHE
+        cubin = Path(os.environ["WOST_CUBIN"]).resolve()
+    else:
+        subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("WOST_LIB", str(ROOT / "dcrmontecarlo_b200" / "libwost.so"))], cwd=td, check=True, capture_output=True)
+        cubin = next(Path(td).glob("*.cubin"))
     dis = subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True, check=True).stdout
 lines, cur, inside = [], ("?", 0), False
 for ln in dis.splitlines():
