@@ -168,7 +168,7 @@ class DCRSurvey:
     def _finish(self, pot, m2, steps, seed, nWalks):
         n = float(nWalks)
         stderr = np.sqrt(m2 / max(n - 1.0, 1.0) / n)
-        M = np.array([r[0] for r in self.receivers]); N = np.array([r[1] for r in self.receivers])
+        M = np.array([r[0] for r in self.receivers], dtype=np.int64); N = np.array([r[1] for r in self.receivers], dtype=np.int64)
         return dict(potentials=pot, stderr=stderr, dV=pot[:, M] - pot[:, N], dV_stderr=np.hypot(stderr[:, M], stderr[:, N]),
                     steps=steps, seed=seed)
 

@@ -63,7 +63,7 @@ def _worker(rank, world, port, P, W, mode, ret):
     pts = torch.arange(2 * P, dtype=torch.float32).reshape(P, 2)
     r = solve_sharded(FakeSolver(), pts, W, seed=11, mode=mode, merge_fn=merge_blocks)
     if rank == world - 1:                                              # every rank holds the full result; check the last one
-        ret["mean"], ret["m2"], ret["steps"] = r["mean"].numpy().copy(), r["m2"].numpy().copy(), r["steps"]
+        ret["mean"], ret["m2"], ret["steps"] = r["mean"].numpy().copy(), r["m2"].numpy().copy(), int(r["steps"])
     dist.barrier()
     dist.destroy_process_group()
 

@@ -22,7 +22,7 @@ def _worker(rank, world, port, key, n_pts, W, ret):
     solver = s.make_solver()
     r = solve_sharded(solver, s.points[:n_pts], W, s.max_steps, s.eps, seed=123)
     if rank == 0:
-        ret["mean"], ret["m2"], ret["steps"], ret["by_points"] = r["mean"].cpu().numpy(), r["m2"].cpu().numpy(), r["steps"], r["by_points"]
+        ret["mean"], ret["m2"], ret["steps"], ret["by_points"] = r["mean"].cpu().numpy(), r["m2"].cpu().numpy(), int(r["steps"]), r["by_points"]
     dist.barrier()
     dist.destroy_process_group()
 
