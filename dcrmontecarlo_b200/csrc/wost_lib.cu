@@ -477,6 +477,22 @@ static void build_wide(const float* xy, int nvtx, float inflate, std::vector<flo
     }
 }
 
+// 1 - 1/I0 table of include/wost_math.h on a device (128 KB, built once per device, kept for the life of the process)
+static const float* iprob_table(int device) {
+    static std::mutex mu; static float* tab[64] = {nullptr};
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tab[device]) {
+        std::vector<float> h(WM_IPROB_N);
+        wm_interior_probability_table(h.data());
+        float* d = nullptr;
+        if (cudaMalloc((void**)&d, sizeof(float) * WM_IPROB_N) != cudaSuccess ||
+            cudaMemcpy(d, h.data(), sizeof(float) * WM_IPROB_N, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+        tab[device] = d;
+    }
+    return tab[device];
+}
+
 static int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return v ? std::atoi(v) : dflt;
@@ -941,6 +957,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.inv_sigma_bar = delta ? (float)(1.0 / (double)P->sigma_bar) : 0.0f;
     a.sqrt_sigma_bar = delta ? (float)std::sqrt((double)P->sigma_bar) : 0.0f;
     a.icdf = s_icdf.dev; a.icdf_len = P->icdf_len;
+    if (delta && !phys_delta && !(a.iprob = iprob_table(scene->device))) return fail(WOST_ERR_ALLOC, "interior-probability table: device allocation failed");
     a.key0 = (uint32_t)P->seed; a.key1 = (uint32_t)(P->seed >> 32);
     a.point_index_base = P->point_index_base; a.walk_offset = P->walk_offset;
     a.walk_vals = vals; a.counter = ctrs; a.steps_total = ctrs + 1;
@@ -975,6 +992,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
             if (!big && scene->n_dseg <= 64 && scene->n_nseg <= 64 && stage_smem == ((d_bytes ? 1 : 0) | (n_bytes ? 2 : 0))) {
                 // small scene: its sizes and query strategy become compile-time constants too
                 fl.n_dseg = scene->n_dseg; fl.n_nseg = scene->n_nseg; fl.sil_coop_max = a.sil_coop_max; fl.ray_coop_max = a.ray_coop_max;
+                fl.stage = stage_smem;
             }
             wost_fields_t none{};
             K = jit::get(fields ? fields : &none, fl, scene->device, mode == 1 || (long long)n_pts * W >= (1ll << 18),
@@ -1190,7 +1208,7 @@ int wost_jit_offline(const wost_field_desc_t* const descs[5] /* g, f, alpha, sig
         *slots[i] = &tmp[i];
     }
     jit::Flags fl{neu != 0, src != 0, delta != 0, trace != 0, phys != 0, big != 0, multi != 0, sp_mode, min_blocks};
-    if (n_dseg >= 0) { fl.n_dseg = n_dseg; fl.n_nseg = n_nseg; coop_thresholds(n_nseg, &fl.sil_coop_max, &fl.ray_coop_max); }
+    if (n_dseg >= 0) { fl.n_dseg = n_dseg; fl.n_nseg = n_nseg; coop_thresholds(n_nseg, &fl.sil_coop_max, &fl.ray_coop_max); fl.stage = 1 | (n_nseg ? 2 : 0); }
     const std::string source = jit::generate(&F, fl);
     const std::string pre = prefix ? prefix : "wost_walk_jit";
     if (FILE* fp = std::fopen((pre + ".cu").c_str(), "w")) { std::fwrite(source.data(), 1, source.size(), fp); std::fclose(fp); }

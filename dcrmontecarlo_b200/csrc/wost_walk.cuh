@@ -18,6 +18,7 @@ struct WalkArgs {
     int max_steps; float eps, rmin;
     int sp_mode; float sigma_bar, inv_sigma_bar, sqrt_sigma_bar;
     const float* icdf; int icdf_len;
+    const float* iprob;                    // 1 - 1/I0(z) on [0, 21]: the table of include/wost_math.h (delta tracking)
     uint32_t key0, key1; long long point_index_base, walk_offset;
     float* walk_vals;
     unsigned long long* counter;           // next unassigned flat walk index
@@ -48,7 +49,7 @@ struct InterpFP {
     static constexpr bool SMF = DELTA || (!NEU && !SRC);
     static constexpr bool STAGE_FIELDS = true;         // copy field headers / terms to shared memory at CTA start
     static constexpr bool MULTI = true;                // shared-walk multi-source code compiled in
-    static constexpr int N_DSEG = -1, N_NSEG = -1, SIL_COOP_MAX = 0, RAY_COOP_MAX = 0;   // scene sizes: run-time values (WalkArgs)
+    static constexpr int N_DSEG = -1, N_NSEG = -1, SIL_COOP_MAX = 0, RAY_COOP_MAX = 0, STAGE = 0;   // scene sizes: run-time values (WalkArgs)
     __device__ __forceinline__ static bool has_g(const WalkArgs& a) { return a.F.g.present != 0; }
     __device__ __forceinline__ static bool has_alpha(const WalkArgs& a) { return a.F.alpha.present != 0; }
     __device__ __forceinline__ static bool has_sigma(const WalkArgs& a) { return a.F.sigma.present != 0; }
@@ -127,15 +128,16 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
     // polylines with a hierarchy are read through L1 by the traversals.  stage_smem: bit 0 Dirichlet, bit 1 Neumann.
     {
         float4* sp = smem + DEVFIELD_F4 * (FIELD_SOURCE0 + a.n_src);
-        if (a.stage_smem & 1) {
+        const int stage_smem = FP::N_DSEG >= 0 ? FP::STAGE : a.stage_smem;   // compile-time in scene-specialised kernels: LDS, not generic loads
+        if (stage_smem & 1) {
             for (int i = threadIdx.x; i < 2 * n_dseg; i += blockDim.x) sp[i] = a.dseg[i];
             dseg = sp; sp += 2 * n_dseg;
         }
-        if (NEU && (a.stage_smem & 2)) {
+        if (NEU && (stage_smem & 2)) {
             for (int i = threadIdx.x; i < 2 * n_nseg; i += blockDim.x) sp[i] = a.nseg[i];
             nseg = sp;
         }
-        if (a.stage_smem) __syncthreads();
+        if (stage_smem) __syncthreads();
     }
     // Terminated walks are parked here (where g is read, the walk's weight and running total, its index) and their
     // boundary term is evaluated later for many lanes at once: evaluated on the spot, g would run with the one or two
@@ -318,8 +320,9 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 // the silhouette distance only matters if it can be smaller than dDirichlet (:212): every Neumann
                 // vertex is at least (|p - c| - R) away, so outside that margin min(dD, dN) = dD without looking.
                 const float gx = x - a.ndisc_x, gy = y - a.ndisc_y;
-                gap = sqrtf(gx * gx + gy * gy) - a.ndisc_r;
-                want_sil = TRACE || !(dD < gap * 0.9999f);
+                const float g2 = gx * gx + gy * gy, lim = dD * 1.001f + a.ndisc_r;   // gap = sqrt(g2) - R > 1.001 dD, without the root
+                if (PHYS) gap = sqrtf(g2) - a.ndisc_r;
+                want_sil = TRACE || !(lim * lim < g2);
                 want_ray = ray_may_hit_disc(ox, oy, ex, ey, a.ndisc_x, a.ndisc_y, a.ndisc_r2);
                 // physical hits are limited to the star radius r <= max(dD, rmin): farther polylines cannot be hit
                 if (PHYS && gap > fmaxf(dD, a.rmin) + a.phys_nudge) want_ray = false;
@@ -520,7 +523,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
             float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f, alpha_s = 1.0f;
             bool have_alpha_s = false;
             if (DELTA && !PHYS) {
-                sbgn = interior_probability(r * a.sqrt_sigma_bar);                      // sigma_bar * |G^sb|(r)
+                sbgn = interior_probability(a.iprob, r * a.sqrt_sigma_bar);                      // sigma_bar * |G^sb|(r)
                 gn = sbgn * a.inv_sigma_bar;                                            // screenedGreensNorm2D (utils.py:29-44)
             }
             if (!PHYS && (SRC || DELTA)) {                                              // :242 (Q10: also without a source)

@@ -22,6 +22,8 @@
  * ---------------------------------------------------------------------------------------- */
 static int g_libm = 0;
 void orc_set_libm(int on) { g_libm = on; }
+static float g_iprob[WM_IPROB_N]; static int g_iprob_ready = 0;   /* 1 - 1/I0 table of include/wost_math.h (filled before the parallel region) */
+static void iprob_init(void) { if (!g_iprob_ready) { wm_interior_probability_table(g_iprob); g_iprob_ready = 1; } }
 static inline float o_expf(float x) { return g_libm ? expf(x) : wm_expf(x); }
 static inline float o_smooth_step(float a) { return g_libm ? 1.0f / (1.0f + expf(a)) : wm_smooth_step(a); }
 static inline void o_sincosf(float a, float* sn, float* cs) {
@@ -484,8 +486,8 @@ static void greens_norm_pair(const orc_params_t* p, float r, int r_is_rmin, doub
             *sbgn = (float)sb * *gn;
         }
     } else {
-        /* the kernel's arithmetic: fp32 throughout, 1 - 1/I0 from include/wost_math.h */
-        *sbgn = wm_interior_probability(r * (float)sqrt(sb));
+        /* the kernel's arithmetic: fp32 throughout, 1 - 1/I0 from the table of include/wost_math.h */
+        *sbgn = wm_interior_probability_lookup(g_iprob, r * (float)sqrt(sb));
         *gn = *sbgn * (float)(1.0 / sb);
     }
 }
@@ -801,6 +803,7 @@ int orc_solve(const orc_params_t* p, const float* pts, int64_t n_pts,
               int64_t n_trace, int32_t trace_cap, float* trace, int32_t* trace_len) {
     const int64_t W = p->n_walks;
     int64_t steps_sum = 0;
+    iprob_init();
     if (p->compat_mode == 1 && (p->rng_mode != ORC_RNG_PHILOX || (p->delta && !(p->sigma_bar > 0.0f)))) return -1;   /* physical: Philox only */
     if (p->rng_mode == ORC_RNG_MT) {
         /* one sequential stream over all points and walks, like the reference; libm / torch elementary functions */

@@ -1,4 +1,20 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest2.log 2>&1; tail -n 4 gpurun_out/r2_pytest2.log
-for c in cfg5_175e cfg4 cfg1b cfg2 cfg3 cfg1a; do WOST_JIT=0 python tools/run_one.py $c 3 | tail -1; WOST_JIT=1 python tools/run_one.py $c 3 | tail -1; done 2>&1 | tee gpurun_out/r2_jit_ab2.log
-WOST_JIT=0 python tools/run_one.py cfg5_175e 3 32768 | tail -1; WOST_JIT=1 python tools/run_one.py cfg5_175e 3 32768 | tail -1
-python tools/small_solve.py 200 2>&1 | tee gpurun_out/r2_small2.log
+python - <<'PY'
+import sys, time, torch
+sys.path.insert(0, '.')
+import bench
+from dcrmontecarlo_b200 import scenarios as sc, _native as nat
+s = sc.cfg4(); solver = s.make_solver()
+pts_h = bench.tile_points(s.points, 16384); pts_d = pts_h.cuda()
+for i in range(6): solver.solve_raw(pts_d, 64, s.max_steps, s.eps, seed=100+i, device_outputs=True)
+torch.cuda.synchronize()
+pin = pts_h.pin_memory()
+for i in range(6): solver.solve_raw(pin, 64, s.max_steps, s.eps, seed=200+i)
+sp_d = s.points.cuda()
+ts = []
+for i in range(60):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = solver.solve_raw(sp_d, 25, s.max_steps, s.eps, seed=300+i, device_outputs=True)
+    torch.cuda.synchronize(); ts.append((time.perf_counter()-t0)*1e6)
+print("per-solve us:", [int(t) for t in ts])
+print(nat.jit_stats())
+PY
