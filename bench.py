@@ -459,7 +459,7 @@ def main():
             "config": {"workload": WORKLOAD, "electrodes": ELECTRODES, "walks_per_electrode": Wg, "walks_per_electrode_per_gpu": WALKS,
                        "walk_steps_per_step": tot_steps / args.steps,
                        "l2_note": "every step uses a fresh Philox key and rewrites its per-walk totals (%d MiB per GPU); the working set is registers / shared memory, not L2" % (ELECTRODES * WALKS * 4 >> 20),
-                       "parallelism": f"distributed.solve_sharded over {world} GPU(s): rank shard = electrodes [{shard.p0},{shard.p1}) x walks [{shard.w0},{shard.w1}); one all_gather_into_tensor of (mean, M2, steps) per step inside the timed region",
+                       "parallelism": f"distributed.solve_sharded over {world} GPU(s): rank 0 shard = electrodes range({shard.p0},{shard.p1},{shard.pstride}) x walks [{shard.w0},{shard.w1}); one all_gather_into_tensor of (mean, M2, steps) per step inside the timed region",
                        "compat": "reference", "specialised_kernel": jit_used, "checksum_last_step": head_checksum},
             "roofline": {"bound": "fp32-issue", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "frac_note": "ALGORITHMIC fp32 flops of the reference's formulation (SURVEY §8(d)) per second over the measured FMA-chain peak: a throughput-equivalent figure, not pipe utilisation; the kernel is bound by instruction issue, see issue_active_frac",
@@ -471,7 +471,7 @@ def main():
                          "peak_source": "FMA-chain microbenchmark in this run (wost_fp32_peak); MEASURED_PEAKS.json has no fp32 entry",
                          "kernel": "wost_walk_jit = walk_body<NEU=1,SRC=1,DELTA=1> specialised for this solver's fields (NVRTC)" if jit_used else "walk_kernel<NEU=1,SRC=1,DELTA=1>",
                          "fp32_peak_effective_sm_mhz": eff_mhz},
-            "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (shard.p1 - shard.p0) * 8 * world,
+            "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": shard.n_points * 8 * world,
                     "d2h_bytes_per_step": (ELECTRODES * 8 + 8) * world, "ms_per_step": e2e_ms / args.steps,
                     "passes_ms_per_step": [p[0] / args.steps for p in e2e_passes]},
             "gpu_launches": n_launch * args.steps * world,

@@ -49,7 +49,7 @@ class SolveParams(C.Structure):
                 ("seed", C.c_uint64), ("point_index_base", C.c_int64), ("walk_offset", C.c_int64), ("compat_mode", C.c_int32),
                 ("majorant_levels", C.c_int32), ("majorant", C.c_void_p),
                 ("majorant_x0", C.c_float), ("majorant_y0", C.c_float), ("majorant_dx", C.c_float), ("majorant_dy", C.c_float),
-                ("jit", C.c_int32)]
+                ("jit", C.c_int32), ("point_index_stride", C.c_int64)]
 
 
 EXPORTS = {
@@ -223,7 +223,7 @@ def _set_majorant(prm, majorant):
 
 def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: float, *, delta: bool = False,
           sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0, point_index_base: int = 0,
-          walk_offset: int = 0, want_block_stats: bool = False, want_walk_vals: bool = False, n_trace: int = 0,
+          walk_offset: int = 0, point_index_stride: int = 1, want_block_stats: bool = False, want_walk_vals: bool = False, n_trace: int = 0,
           trace_cap: int = 0, device_outputs: bool = False, compat: str = "reference", majorant=None, jit: str = "auto",
           out: dict | None = None):
     """One wost_solve call.  ``pts`` may be a host array/tensor or a CUDA tensor on the scene's device.
@@ -246,7 +246,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
     prm.compat_mode = COMPAT[compat]
-    prm.jit = JIT[jit]
+    prm.jit, prm.point_index_stride = JIT[jit], int(point_index_stride)
     maj_keep = _set_majorant(prm, majorant)
 
     if device_outputs:
@@ -283,7 +283,7 @@ def solve(scene: Scene, fields: Fields, pts, n_walks: int, max_steps: int, eps: 
 
 def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int, max_steps: int, eps: float, *,
                        delta: bool = False, sp_mode: int = SP_FULL, sigma_bar: float = 0.0, icdf=None, seed: int = 0,
-                       point_index_base: int = 0, walk_offset: int = 0, want_block_stats: bool = False,
+                       point_index_base: int = 0, walk_offset: int = 0, point_index_stride: int = 1, want_block_stats: bool = False,
                        device_outputs: bool = False, compat: str = "reference", majorant=None, jit: str = "auto"):
     """One wost_solve_multi_source call: shared walks, one estimate per (source, point).  ``sources`` is a list of
     DeviceField.  Returns mean / m2 of shape (S, P)."""
@@ -303,7 +303,7 @@ def solve_multi_source(scene: Scene, fields: Fields, sources, pts, n_walks: int,
         prm.screened_icdf, prm.icdf_len = ptr(icdf_keep).value, int(icdf_keep.shape[0])
     prm.seed, prm.point_index_base, prm.walk_offset = int(seed) & (2 ** 64 - 1), int(point_index_base), int(walk_offset)
     prm.compat_mode = COMPAT[compat]
-    prm.jit = JIT[jit]
+    prm.jit, prm.point_index_stride = JIT[jit], int(point_index_stride)
     maj_keep = _set_majorant(prm, majorant)
     handles = (C.c_void_p * S)(*[s.handle for s in sources])
     if device_outputs:

@@ -849,7 +849,9 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     if (!scene || !P || !pts_xy) return fail(WOST_ERR_INVALID, "scene, params and pts_xy are required");
     if (n_pts < 0 || P->n_walks <= 0 || P->max_steps < 0) return fail(WOST_ERR_INVALID, "n_pts >= 0, n_walks > 0, max_steps >= 0 required");
     if (!(P->eps >= 0.0f)) return fail(WOST_ERR_INVALID, "eps must be >= 0");
-    if (n_pts >= (1ll << 32) || P->n_walks + P->walk_offset >= (1ll << 32) || n_pts + P->point_index_base >= (1ll << 32))
+    const long long pstride = P->point_index_stride > 0 ? P->point_index_stride : 1;
+    if (P->point_index_stride < 0) return fail(WOST_ERR_INVALID, "point_index_stride must be >= 0");
+    if (n_pts >= (1ll << 32) || P->n_walks + P->walk_offset >= (1ll << 32) || (n_pts - 1) * pstride + P->point_index_base >= (1ll << 32))
         return fail(WOST_ERR_INVALID, "point and walk indices must fit 32 bits (Philox counter words)");
     const bool delta = P->delta_tracking != 0;
     if (P->compat_mode != WOST_COMPAT_REFERENCE && P->compat_mode != WOST_COMPAT_PHYSICAL) return fail(WOST_ERR_INVALID, "unknown compat_mode");
@@ -959,7 +961,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.icdf = s_icdf.dev; a.icdf_len = P->icdf_len;
     if (delta && !phys_delta && !(a.iprob = iprob_table(scene->device))) return fail(WOST_ERR_ALLOC, "interior-probability table: device allocation failed");
     a.key0 = (uint32_t)P->seed; a.key1 = (uint32_t)(P->seed >> 32);
-    a.point_index_base = P->point_index_base; a.walk_offset = P->walk_offset;
+    a.point_index_base = P->point_index_base; a.point_index_stride = pstride; a.walk_offset = P->walk_offset;
     a.walk_vals = vals; a.counter = ctrs; a.steps_total = ctrs + 1;
     a.ndisc_x = scene->ndisc_x; a.ndisc_y = scene->ndisc_y; a.ndisc_r = scene->ndisc_r; a.ndisc_r2 = scene->ndisc_r2;
     coop_thresholds(scene->n_nseg, &a.sil_coop_max, &a.ray_coop_max);
@@ -1023,7 +1025,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
         a.chunk = (int)(chunk < 32 ? 32 : (chunk > 1024 ? 1024 : chunk));
         if (total < nwarps * 32) a.chunk = (int)((total + nwarps - 1) / nwarps);
         if (a.chunk < 1) a.chunk = 1;
-        a.pts = s_pts.dev + 2 * p0; a.n_pts = np; a.point_index_base = P->point_index_base + p0;
+        a.pts = s_pts.dev + 2 * p0; a.n_pts = np; a.point_index_base = P->point_index_base + p0 * pstride;
         a.alpha0 = alpha0 ? alpha0 + p0 : nullptr;
         a.walk_vals = vals_dev_out ? out_walk_vals + (size_t)p0 * W : vals;
         if (trace) {                                                    // the first n_trace walks in point-major order

@@ -19,7 +19,7 @@ struct WalkArgs {
     int sp_mode; float sigma_bar, inv_sigma_bar, sqrt_sigma_bar;
     const float* icdf; int icdf_len;
     const float* iprob;                    // 1 - 1/I0(z) on [0, 21]: the table of include/wost_math.h (delta tracking)
-    uint32_t key0, key1; long long point_index_base, walk_offset;
+    uint32_t key0, key1; long long point_index_base, point_index_stride, walk_offset;   // global index of point p: base + p * stride
     float* walk_vals;
     unsigned long long* counter;           // next unassigned flat walk index
     unsigned long long* steps_total;
@@ -187,7 +187,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                     const uint32_t p32 = (uint32_t)id / (uint32_t)a.n_walks;
                     p = p32; w = (uint32_t)id - p32 * (uint32_t)a.n_walks;
                 } else { p = id / (unsigned long long)a.n_walks; w = id - p * (unsigned long long)a.n_walks; }
-                pidx = (uint32_t)(a.point_index_base + (long long)p); widx = (uint32_t)(a.walk_offset + (long long)w);
+                pidx = (uint32_t)(a.point_index_base + (long long)p * a.point_index_stride); widx = (uint32_t)(a.walk_offset + (long long)w);
                 x = __ldg(a.pts + 2 * p); y = __ldg(a.pts + 2 * p + 1);
                 dD = 1.0f;                                             // :190 sentinel (Q6)
                 atten = 1.0f; total_v = 0.0f; onB = false; phi_n = 0.0f; steps = 0;   // :188-195

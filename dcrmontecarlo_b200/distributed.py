@@ -3,8 +3,9 @@
 Every (evaluation point, walk) pair is independent (reference ``solvers/WoStSolver.py:182-187`` loops over them
 sequentially), and the Philox counters are *global* (point, walk, step) indices, so the work shards freely:
 
-* by evaluation points (electrode positions) when they divide evenly enough — each rank solves a contiguous slice with
-  all walks;
+* by evaluation points (electrode positions) when they divide evenly enough — rank r solves points r, r + world, ...
+  with all walks (interleaved rather than contiguous slices: walk lengths depend on where a point lies, and neighbouring
+  points cost about the same, so every rank gets the same mix);
 * by walk ranges, on boundaries of the deterministic reduction block (``WOST_WALK_BLOCK`` walks), when there are fewer
   points than ranks or the points would balance badly (e.g. the 9-electrode DCR line on 8 GPUs) — each rank solves all
   points for a slice of the walks.
@@ -29,15 +30,17 @@ WALK_BLOCK = 1024
 
 @dataclass(frozen=True)
 class Shard:
+    """Points ``range(p0, p1, pstride)`` x walks ``[w0, w1)``."""
     rank: int
     p0: int
     p1: int
     w0: int
     w1: int
+    pstride: int = 1
 
     @property
     def n_points(self):
-        return self.p1 - self.p0
+        return len(range(self.p0, self.p1, self.pstride))
 
     @property
     def n_walks(self):
@@ -55,22 +58,26 @@ def _split(n: int, parts: int):
 def shard_plan(n_points: int, n_walks: int, world: int, mode: str = "auto") -> list[Shard]:
     """Work split for ``world`` ranks.  ``mode``: 'points', 'walks' or 'auto'.
 
-    'auto' shards points when there are at least as many as ranks and they balance (an even split, or >= 16 points per
-    rank so that one extra point costs at most 6 %); otherwise walk ranges when every rank can get a whole reduction
-    block; otherwise points."""
+    'auto' looks for an even split: points if they divide by the number of ranks; else whole reduction blocks of walks if
+    THEY divide (and the gathered block statistics stay small); else points when there are >= 16 per rank (one extra
+    point costs at most 6 %), else walks, else points."""
     if world < 1:
         raise ValueError("world must be >= 1")
     nblk = (n_walks + WALK_BLOCK - 1) // WALK_BLOCK
     if mode == "auto":
-        if n_points >= world and (n_points % world == 0 or n_points >= 16 * world):
+        small_gather = n_points * ((nblk + world - 1) // world) * 16 <= (8 << 20)
+        if n_points >= world and n_points % world == 0:
             mode = "points"
-        elif nblk >= world and (nblk % world == 0 or nblk >= 16 * world or n_points < world):
+        elif nblk >= world and nblk % world == 0 and small_gather:
+            mode = "walks"
+        elif n_points >= 16 * world:
+            mode = "points"
+        elif nblk >= world and small_gather:
             mode = "walks"
         else:
             mode = "points" if n_points >= world else "walks"
     if mode == "points":
-        e = _split(n_points, world)
-        return [Shard(r, e[r], e[r + 1], 0, n_walks) for r in range(world)]
+        return [Shard(r, min(r, n_points), n_points, 0, n_walks, world) for r in range(world)]
     if mode == "walks":
         e = _split(nblk, world)                                        # whole reduction blocks per rank
         return [Shard(r, 0, n_points, min(e[r] * WALK_BLOCK, n_walks), min(e[r + 1] * WALK_BLOCK, n_walks)) for r in range(world)]
@@ -102,10 +109,12 @@ class _Layout:
             self.pmax = max(max(sh.n_points for sh in self.plan), 1)
             self.send = torch.zeros(3, self.pmax, **f64)
             self.recv = torch.empty(world, 3, self.pmax, **f64)
-            idx = [sh.rank * 3 * self.pmax + k for sh in self.plan for k in range(sh.n_points)]
-            self.idx_mean = torch.tensor(idx, dtype=torch.int64, device=device)
+            where = {}
+            for sh in self.plan:
+                for k, p in enumerate(range(sh.p0, sh.p1, sh.pstride)):
+                    where[p] = sh.rank * 3 * self.pmax + k
+            self.idx_mean = torch.tensor([where[p] for p in range(P)], dtype=torch.int64, device=device)
             self.idx_m2 = self.idx_mean + self.pmax
-            self.even = all(sh.n_points == self.pmax for sh in self.plan)
         else:
             # per rank: (P, bmax, 2) block statistics, then one trailing slot with the step count
             self.bmax = max(max((sh.n_walks + WALK_BLOCK - 1) // WALK_BLOCK for sh in self.plan), 1)
@@ -158,14 +167,15 @@ def solve_sharded(solver, points: torch.Tensor, nWalks: int, maxSteps: int = 100
 
     if L.by_points:
         if have_work:
+            mine = pts[me.p0:me.p1:me.pstride].contiguous()
             if native_out:
                 out = dict(mean=L.send[0, : me.n_points], m2=L.send[1, : me.n_points], steps=L.steps_i64)
-                solver.solve_raw(pts[me.p0:me.p1], me.n_walks, maxSteps, eps, seed=seed, point_index_base=me.p0, walk_offset=me.w0,
-                                 want_block_stats=False, device_outputs=True, out=out)
+                solver.solve_raw(mine, me.n_walks, maxSteps, eps, seed=seed, point_index_base=me.p0, point_index_stride=me.pstride,
+                                 walk_offset=me.w0, want_block_stats=False, device_outputs=True, out=out)
                 L.send[2, 0] = L.steps_i64[0]                                # int64 -> fp64 on the device (exact below 2^53)
             else:
-                r = solver.solve_raw(pts[me.p0:me.p1], me.n_walks, maxSteps, eps, seed=seed, point_index_base=me.p0, walk_offset=me.w0,
-                                     want_block_stats=False, device_outputs=on_gpu)
+                r = solver.solve_raw(mine, me.n_walks, maxSteps, eps, seed=seed, point_index_base=me.p0, point_index_stride=me.pstride,
+                                     walk_offset=me.w0, want_block_stats=False, device_outputs=on_gpu)
                 L.send[0, : me.n_points] = _as_tensor(r["mean"], device, torch.float64)
                 L.send[1, : me.n_points] = _as_tensor(r["m2"], device, torch.float64)
                 L.send[2, 0] = float(_as_tensor(r["steps"], device).reshape(-1)[0])
@@ -175,11 +185,8 @@ def solve_sharded(solver, points: torch.Tensor, nWalks: int, maxSteps: int = 100
             dist.all_gather_into_tensor(L.recv.view(-1), L.send.view(-1), group=group)
         else:
             L.recv[0].copy_(L.send)
-        if L.even:
-            mean, m2 = L.recv[:, 0, :].reshape(-1), L.recv[:, 1, :].reshape(-1)
-        else:
-            flat = L.recv.reshape(-1)
-            mean, m2 = flat.index_select(0, L.idx_mean), flat.index_select(0, L.idx_m2)
+        flat = L.recv.reshape(-1)
+        mean, m2 = flat.index_select(0, L.idx_mean), flat.index_select(0, L.idx_m2)
         steps = L.recv[:, 2, 0].sum().to(torch.int64)
     else:
         if have_work:

@@ -379,7 +379,7 @@ class WostSolver_2D:
     # solve (reference :319-353)
     # ------------------------------------------------------------------------------------------------
     def solve_raw(self, solvePoints, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None, point_index_base=0,
-                  walk_offset=0, want_block_stats=False, want_walk_vals=False, n_trace=0, trace_cap=0,
+                  point_index_stride=1, walk_offset=0, want_block_stats=False, want_walk_vals=False, n_trace=0, trace_cap=0,
                   device_outputs=False, device=None, jit=None, out=None):
         """One kernel pass over ``solvePoints`` on one device; returns the raw statistics dict
         (mean, m2, steps, optional block_stats / walk_vals / trace).  Building block of :meth:`solve`
@@ -392,7 +392,8 @@ class WostSolver_2D:
         res = nat.solve(scene, fields, solvePoints, int(nWalks), int(maxSteps), float(eps),
                         delta=self.use_delta_tracking, sp_mode=self.sp_mode,
                         sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
-                        point_index_base=point_index_base, walk_offset=walk_offset, want_block_stats=want_block_stats,
+                        point_index_base=point_index_base, point_index_stride=point_index_stride, walk_offset=walk_offset,
+                        want_block_stats=want_block_stats,
                         want_walk_vals=want_walk_vals, n_trace=n_trace, trace_cap=trace_cap, device_outputs=device_outputs,
                         compat=self.compat, majorant=self._device_majorant(device), jit=jit or self.jit, out=out)
         res["seed"] = seed
@@ -400,7 +401,7 @@ class WostSolver_2D:
 
     def solve_multi_source(self, solvePoints, sources, nWalks=1000, maxSteps=1000, eps=1e-4, *, seed=None,
                            want_block_stats=False, device_outputs=False, device=None, jit=None, point_index_base=0,
-                           walk_offset=0):
+                           point_index_stride=1, walk_offset=0):
         """Shared-walk solve for many source terms (not in the reference, which re-walks per source): the walk does not
         depend on ``f``, so one set of walks gives the estimate for every source in ``sources`` (callables or fields).
         Returns ``mean`` / ``m2`` of shape ``(len(sources), P)``; row ``s`` equals what :meth:`solve_raw` returns with
@@ -408,13 +409,21 @@ class WostSolver_2D:
         nat.require_cuda()
         device = nat.current_device() if device is None else int(device)
         scene, fields, icdf, keep = self._device_problem(device)
-        devs = [self._dev_field(f, device) for f in sources]
+        if all(isinstance(f, Field) for f in sources):                   # immutable field objects: one lookup for the whole list
+            key = ("dev_sources", device, tuple(map(id, sources)))
+            hit = self._cache.get(key)
+            if hit is None:
+                hit = self._cache[key] = (list(sources), [self._dev_field(f, device) for f in sources])
+            devs = hit[1]
+        else:
+            devs = [self._dev_field(f, device) for f in sources]
         if seed is None:
             seed = _next_seed()
         res = nat.solve_multi_source(scene, fields, devs, solvePoints, int(nWalks), int(maxSteps), float(eps),
                                      delta=self.use_delta_tracking, sp_mode=self.sp_mode,
                                      sigma_bar=float(self.sigma_bar) if self.use_delta_tracking else 0.0, icdf=icdf, seed=seed,
-                                     point_index_base=point_index_base, walk_offset=walk_offset,
+                                     point_index_base=point_index_base, point_index_stride=point_index_stride,
+                                     walk_offset=walk_offset,
                                      want_block_stats=want_block_stats, device_outputs=device_outputs, compat=self.compat,
                                      majorant=self._device_majorant(device), jit=jit or self.jit)
         res["seed"] = seed

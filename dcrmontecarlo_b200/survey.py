@@ -139,29 +139,28 @@ class DCRSurvey:
         global electrode index, so the numbers do not depend on the number of ranks."""
         import torch.distributed as dist
 
-        from .distributed import _split
-
         S, E = len(self.sources), self.electrodes.shape[0]
-        edges = _split(E, world)
-        e0, e1 = edges[rank], edges[rank + 1]
-        emax = max(edges[r + 1] - edges[r] for r in range(world))
+        # rank r takes electrodes r, r + world, ...: the cost of an electrode depends on how many current electrodes its
+        # walks pass, which varies along the line, so interleaved subsets balance where contiguous chunks would not
+        mine = self.electrodes[rank::world].contiguous()
+        n_mine, emax = mine.shape[0], (E + world - 1) // world
         use_cuda = torch.cuda.is_available() and hasattr(self.solver, "_device_problem")
         dev = torch.device("cuda", torch.cuda.current_device()) if (on_nccl or (world == 1 and use_cuda)) else torch.device("cpu")
         send = torch.zeros(2 * S * emax + 1, dtype=torch.float64, device=dev)
-        if e1 > e0:
-            r = self.solver.solve_multi_source(self.electrodes[e0:e1], self._fields, nWalks, maxSteps, eps, seed=seed,
-                                               point_index_base=e0, device_outputs=dev.type == "cuda")
+        if n_mine > 0:
+            r = self.solver.solve_multi_source(mine, self._fields, nWalks, maxSteps, eps, seed=seed, point_index_base=rank,
+                                               point_index_stride=world, device_outputs=dev.type == "cuda")
             as_t = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dev)   # noqa: E731
             blk = send[: 2 * S * emax].view(2, S, emax)
-            blk[0, :, : e1 - e0], blk[1, :, : e1 - e0] = as_t(r["mean"]), as_t(r["m2"])
+            blk[0, :, :n_mine], blk[1, :, :n_mine] = as_t(r["mean"]), as_t(r["m2"])
             send[2 * S * emax] = as_t(r["steps"]).reshape(-1)[0].to(torch.float64)
         if world > 1:
             recv = torch.empty(world, 2 * S * emax + 1, dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(recv.view(-1), send, group=None)
         else:
             recv = send.view(1, -1)
-        parts = [recv[q, : 2 * S * emax].view(2, S, emax)[:, :, : edges[q + 1] - edges[q]] for q in range(world)]
-        full = torch.cat(parts, dim=2).cpu().numpy()                       # (2, S, E): the one host read of the run
+        # (world, 2, S, emax) -> electrode e = slot * world + rank
+        full = recv[:, : 2 * S * emax].view(world, 2, S, emax).permute(1, 2, 3, 0).reshape(2, S, emax * world)[:, :, :E].cpu().numpy()
         steps = int(recv[:, 2 * S * emax].sum().item())
         return self._finish(full[0], full[1], steps, seed, nWalks)
 

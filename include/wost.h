@@ -133,6 +133,9 @@ typedef struct {
      * unavailable), 2 = never.  The environment variable WOST_JIT (0 / 1) overrides; WOST_JIT_CACHE=<dir> keeps compiled
      * kernels on disk. */
     int32_t jit;
+    /* pts[k] has the global index point_index_base + k * point_index_stride (0 is read as 1): a rank of a multi-GPU job
+     * that owns every world-th evaluation point passes base = rank, stride = world. */
+    int64_t point_index_stride;
 } wost_solve_params_t;
 
 #define WOST_WALK_BLOCK 1024   /* walks per deterministic reduction block */

@@ -49,9 +49,11 @@ def merge_blocks(blocks, n_walks):
 
 
 class FakeSolver:
-    def solve_raw(self, pts, nWalks, maxSteps, eps, *, seed, point_index_base, walk_offset, want_block_stats, device_outputs):
+    def solve_raw(self, pts, nWalks, maxSteps, eps, *, seed, point_index_base, walk_offset, want_block_stats, device_outputs,
+                  point_index_stride=1):
         P = len(pts)
-        vals = np.array([[walk_value(point_index_base + p, walk_offset + w, seed) for w in range(nWalks)] for p in range(P)], np.float32)
+        assert all(float(pts[k][0]) == 2.0 * (point_index_base + k * point_index_stride) for k in range(P)) or float(np.abs(np.asarray(pts)).max()) == 0.0
+        vals = np.array([[walk_value(point_index_base + p * point_index_stride, walk_offset + w, seed) for w in range(nWalks)] for p in range(P)], np.float32)
         bs = block_stats(vals)
         mean, m2 = merge_blocks(bs, nWalks)
         return dict(mean=mean, m2=m2, block_stats=bs, steps=np.array([P * nWalks * 3], np.uint64), n=nWalks)
@@ -90,7 +92,7 @@ def test_shard_plan_covers_everything_once():
         assert len(plan) == world
         seen = np.zeros((P, W), np.int32)
         for sh in plan:
-            seen[sh.p0:sh.p1, sh.w0:sh.w1] += 1
+            seen[sh.p0:sh.p1:sh.pstride, sh.w0:sh.w1] += 1
             assert sh.n_walks == 0 or sh.w0 % WALK_BLOCK == 0          # walk shards start on reduction-block boundaries
         assert np.all(seen == 1)
         by_points = all(sh.w0 == 0 and sh.w1 == W for sh in plan)
@@ -108,9 +110,9 @@ def test_shard_plan_covers_everything_once():
 class FakeSurveySolver:
     """Stand-in for WostSolver_2D inside DCRSurvey: values depend on GLOBAL (source, electrode) indices only."""
 
-    def solve_multi_source(self, pts, sources, nWalks, maxSteps, eps, *, seed, point_index_base=0, device_outputs=False):
+    def solve_multi_source(self, pts, sources, nWalks, maxSteps, eps, *, seed, point_index_base=0, point_index_stride=1, device_outputs=False):
         S, E = len(sources), len(pts)
-        mean = np.array([[np.float64(walk_value(point_index_base + e, s, seed)) for e in range(E)] for s in range(S)])
+        mean = np.array([[np.float64(walk_value(point_index_base + e * point_index_stride, s, seed)) for e in range(E)] for s in range(S)])
         return dict(mean=mean, m2=np.abs(mean) * 3.0, steps=np.array([S * E * nWalks], np.uint64))
 
 

@@ -37,7 +37,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(nat._Term) == 64
     assert C.sizeof(nat.FieldDesc) == 80                                    # 60 bytes of scalars, padded to 64, two pointers
     assert C.sizeof(nat.Fields) == 40
-    assert C.sizeof(nat.SolveParams) == 112
+    assert C.sizeof(nat.SolveParams) == 120
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the behaviour WITHOUT a GPU")
