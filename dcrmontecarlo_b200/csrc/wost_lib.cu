@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 using namespace wost;
@@ -973,7 +974,6 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.maj.x0 = P->majorant_x0; a.maj.y0 = P->majorant_y0; a.maj.dx = P->majorant_dx; a.maj.dy = P->majorant_dy;
     a.n_trace = trace ? n_trace : 0; a.trace_cap = trace_cap; a.trace = s_trace.dev; a.trace_len = s_tlen.dev;
 
-    const int threads = 256;
     a.stage_smem = stage_smem;
     const bool phys = P->compat_mode == WOST_COMPAT_PHYSICAL;
     const bool big = scene->dbvh != nullptr || scene->nbvh != nullptr;
@@ -1009,16 +1009,43 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     }
     const auto T1 = t_now();
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    int occ = 0, occ_small = 0;                                         // resident CTAs per SM: 256 threads / one-warp CTAs (small jobs)
+    const int small_wps = env_int("WOST_SMALL_WARPS_PER_SCHEDULER", 2), forced_lanes = env_int("WOST_LANES_PER_WARP", 0);
+    {
+        static std::mutex mu;                                           // the query costs microseconds: once per (kernel, shared memory)
+        static std::map<std::tuple<const void*, size_t, int>, std::pair<int, int>> cache;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find({kern, smem, scene->device});
+        if (it == cache.end()) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_small, kern, 32, smem));
+            it = cache.emplace(std::make_tuple(kern, smem, scene->device), std::make_pair(occ, occ_small)).first;
+        }
+        occ = it->second.first; occ_small = it->second.second;
+    }
     const auto T2 = t_now();
     if (occ < 1) return fail(WOST_ERR_CUDA, "walk kernel does not fit on an SM");
     { const int cap = env_int("WOST_MAX_CTAS_PER_SM", 0); if (cap > 0 && occ > cap) occ = cap; }   // experiments: fewer resident warps
     for (long long p0 = 0; p0 < n_pts; p0 += pts_per_pass) {
         const long long np = std::min(pts_per_pass, (long long)n_pts - p0);
         const long long total = np * W;
-        long long grid = (long long)scene->sm_count * occ;             // persistent: one wave, a multiple of the SM count
-        const long long want = (total + threads - 1) / threads;
+        // Small jobs are latency-bound: the solve takes as long as its longest walk, and walks that share a warp wait for
+        // each other's divergent branches.  A job that cannot fill the machine deals its walks to fewer lanes per warp
+        // (about `small_wps` warps per SM scheduler) in one-warp CTAs, which the block scheduler spreads over all SMs.
+        int lanes = 32, threads = 256, occ_l = occ;
+        {
+            const long long slots = (long long)scene->sm_count * 4 * small_wps;            // warps the small-job layout uses
+            if (total < slots * 32) {
+                lanes = 1;
+                while (lanes < 32 && total > slots * lanes) lanes *= 2;
+            }
+            if (forced_lanes >= 1 && forced_lanes <= 32) lanes = forced_lanes;
+            if (lanes < 32) { threads = 32; occ_l = occ_small; }
+        }
+        a.lanes = lanes;
+        long long grid = (long long)scene->sm_count * occ_l;           // persistent: one wave, a multiple of the SM count
+        const long long per_cta = (long long)lanes * (threads / 32);
+        const long long want = (total + per_cta - 1) / per_cta;
         if (grid > want) grid = want;
         const long long nwarps = grid * (threads / 32);
         long long chunk = total / (nwarps * 8);

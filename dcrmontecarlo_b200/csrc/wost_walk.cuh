@@ -24,6 +24,8 @@ struct WalkArgs {
     unsigned long long* counter;           // next unassigned flat walk index
     unsigned long long* steps_total;
     int chunk;                             // walks a warp reserves per atomic
+    int lanes;                             // lanes of a warp that take walks (32; fewer for small jobs: walks that do not share
+                                           // a warp do not wait for each other's divergent branches, see solve_impl)
     float ndisc_x, ndisc_y, ndisc_r, ndisc_r2;   // disc enclosing the Neumann polyline (inflated), for culling
     int sil_coop_max, ray_coop_max;        // answer a query cooperatively when at most this many lanes need it
     Bvh dbvh, nbvh; float bvh_slack;       // hierarchies for large polylines (nodes == nullptr: brute force)
@@ -155,7 +157,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
     bool flush_now = false;                    // warp-uniform: a lane terminated again while still parked
 
     // per-lane walk state
-    bool active = false, retired = false;
+    bool active = false, retired = lane >= a.lanes;
     unsigned long long id = 0; uint32_t pidx = 0, widx = 0;
     float x = 0.f, y = 0.f, dD = 1.0f, atten = 1.0f, total_v = 0.0f, phi_n = 0.0f;
     float alpha_x = 1.0f;                      // alpha at the walker's position (delta tracking), carried from step to step

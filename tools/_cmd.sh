@@ -1,16 +1,12 @@
-python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2_pytest_multi.log 2>&1; tail -n 5 gpurun_out/r2_pytest_multi.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --quick > gpurun_out/r2_bench2_quick.json 2> gpurun_out/r2_bench2_quick.err; echo rc=$?; tail -c 1500 gpurun_out/r2_bench2_quick.err
-python bench.py --gpus 1 --steps 5 --warmup 3 --quick --no-cpu-baseline > gpurun_out/r2_bench1_quick.json 2> gpurun_out/r2_bench1_quick.err; echo rc=$?
-python - <<'PY'
-import json
-for f in ('gpurun_out/r2_bench1_quick.json','gpurun_out/r2_bench2_quick.json'):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1])
-    except Exception as e:
-        print(f, 'ERR', e); continue
-    print(f, {k:d[k] for k in ('value','ms_per_step','n_gpus')}, 'e2e %.3e'%d['e2e']['value'])
-    for k,v in d['strong_scaling'].items(): print('  ', k, v['ms'], v['checksum'], v['sharding'])
-    for k,v in d['rmse_vs_time'].items(): print('  ', k, [(x['walks'], round(x['wall_s']*1e6), x['checksum']) for x in v])
-    if 'configs' in d:
-        for k,v in d['configs'].items(): print('  ', k, '%.3e'%v['steps_per_s'], v['shipped_size']['device_resident_us_blocks'], v['shipped_size']['host_buffers_us_blocks'])
-PY
+set -x
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2b_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2b_pytest_gpu.log
+# small-solve layout sweep
+for L in 32 0 1 2 4 8; do echo "== WOST_LANES_PER_WARP=$L"; WOST_LANES_PER_WARP=$L python tools/small_solve.py 100 2>&1 | grep '"jit": true\| on '; done > gpurun_out/r2b_small_sweep.txt 2>&1
+for S in 1 4; do echo "== auto, WOST_SMALL_WARPS_PER_SCHEDULER=$S"; WOST_SMALL_WARPS_PER_SCHEDULER=$S python tools/small_solve.py 100 2>&1 | grep ' on '; done >> gpurun_out/r2b_small_sweep.txt 2>&1
+# steps of the profiled passes (seed = pass index) and occupancy A/B
+for s in cfg5 cfg5_175e cfg4 cfg2 cfg1b cfg1a cfg3; do python tools/run_one.py $s 4; done > gpurun_out/r2b_run_one.txt 2>&1
+for mb in 4 5 6; do for s in cfg5 cfg4 cfg2 cfg1b; do echo -n "minblocks=$mb "; WOST_JIT_MIN_BLOCKS=$mb python tools/run_one.py $s 4 | tail -1; done; done > gpurun_out/r2b_minblocks.txt 2>&1
+for s in cfg5 cfg1a cfg3; do
+  timeout 600 ncu --set full --clock-control none -k regex:walk --launch-skip 2 -c 1 -f -o gpurun_out/r2_full_$s python tools/run_one.py $s 4 > gpurun_out/r2_ncu_full_$s.log 2>&1
+done
+ls gpurun_out
