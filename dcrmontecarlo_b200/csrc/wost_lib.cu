@@ -86,6 +86,8 @@ struct wost_scene {
     float4* nseg_as_dir = nullptr;                     //   primitive entry points (intersect on `which = 0`, distance on `which = 1`)
     mutable std::mutex arena_mu;
     mutable std::map<cudaStream_t, Arena> arenas;      // per stream (a scene may be used from several streams at once)
+    // shared-walk solves: the source grid (wost_walk.cuh, SourceGrid) of each source set used with this scene, by field ids
+    mutable std::map<std::vector<uint64_t>, SourceGrid> source_grids;
     Arena* arena_for(cudaStream_t st) const {
         std::lock_guard<std::mutex> lk(arena_mu);
         Arena& a = arenas[st];
@@ -709,6 +711,7 @@ int wost_scene_destroy(wost_scene_t* s) {
     cudaFree(s->nwide_boxes); cudaFree(s->nwide_cones); cudaFree(s->dwide_boxes);
     cudaFree(s->dseg_as_neu); cudaFree(s->nseg_as_dir);
     for (auto& kv : s->arenas) kv.second.release();
+    for (auto& kv : s->source_grids) cudaFree((void*)kv.second.masks);
     delete s;
     return WOST_OK;
 }
@@ -843,6 +846,54 @@ int wost_sigma_prime_eval(const wost_fields_t* F, int32_t sp_mode, const float* 
 }  // extern "C"
 
 // Shared implementation of wost_solve (n_sources == 0: the source is fields->f) and wost_solve_multi_source.
+// Source grid of a shared-walk solve (SourceGrid, wost_walk.cuh): built once per (scene, source set) and kept with the scene.
+// Returns a grid with masks == nullptr when binning cannot help (no source with compact support).
+static int source_grid_for(const wost_scene_t* scene, const wost_field_t* const* sources, int n, SourceGrid* out) {
+    SourceGrid none{}; *out = none;
+    std::vector<uint64_t> key(n);
+    for (int k = 0; k < n; ++k) key[k] = sources[k]->uid;
+    std::lock_guard<std::mutex> lk(scene->arena_mu);
+    auto it = scene->source_grids.find(key);
+    if (it != scene->source_grids.end()) { *out = it->second; return WOST_OK; }
+    if (scene->source_grids.size() >= 64) return WOST_OK;               // bounded (grids live as long as the scene): test every disc instead
+    // discs outside which each term is exactly zero (exp argument below -110: wost_device.cuh, term_value); a source without
+    // compact support is listed everywhere
+    struct Disc { int k; double x, y, r; };
+    std::vector<Disc> discs; std::vector<char> everywhere(n, 0);
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int k = 0; k < n; ++k) {
+        if (!(sources[k]->support.z < 1.0e38f)) { everywhere[k] = 1; continue; }
+        for (const wost_term_t& t : sources[k]->h_terms) {
+            const double r = std::sqrt(112.0 / (double)t.q) * 1.001 + 1e-6;
+            discs.push_back({k, t.cx, t.cy, r});
+            x0 = std::min(x0, t.cx - r); x1 = std::max(x1, t.cx + r); y0 = std::min(y0, t.cy - r); y1 = std::max(y1, t.cy + r);
+        }
+    }
+    if (discs.empty()) { scene->source_grids[key] = none; return WOST_OK; }
+    SourceGrid g{};
+    g.nx = 64; g.ny = 64; g.words = (n + 63) / 64;
+    const double dx = std::max((x1 - x0) / g.nx, 1e-30), dy = std::max((y1 - y0) / g.ny, 1e-30);
+    g.x0 = (float)x0; g.y0 = (float)y0; g.inv_dx = (float)(1.0 / dx); g.inv_dy = (float)(1.0 / dy);
+    std::vector<unsigned long long> m(((size_t)g.nx * g.ny + 1) * g.words, 0ull);
+    auto set = [&](size_t cell, int k) { m[cell * g.words + k / 64] |= 1ull << (k % 64); };
+    for (int k = 0; k < n; ++k) if (everywhere[k]) for (size_t c = 0; c <= (size_t)g.nx * g.ny; ++c) set(c, k);
+    for (const Disc& d : discs) {                                       // the disc's box plus one cell all round (fp32 cell lookup)
+        const int i0 = std::max(0, (int)std::floor((d.x - d.r - x0) / dx) - 1), i1 = std::min(g.nx - 1, (int)std::floor((d.x + d.r - x0) / dx) + 1);
+        const int j0 = std::max(0, (int)std::floor((d.y - d.r - y0) / dy) - 1), j1 = std::min(g.ny - 1, (int)std::floor((d.y + d.r - y0) / dy) + 1);
+        for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) set((size_t)j * g.nx + i, d.k);
+    }
+    unsigned long long* dm = nullptr;
+    if (cudaMalloc((void**)&dm, m.size() * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemcpy(dm, m.data(), m.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(dm);
+        return fail(WOST_ERR_ALLOC, "source grid: device allocation failed");
+    }
+    g.masks = dm;
+    scene->source_grids[key] = g;
+    *out = g;
+    return WOST_OK;
+}
+
 static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, const wost_field_t* const* sources, int n_sources,
                       const wost_solve_params_t* P, const float* pts_xy, int64_t n_pts,
                       double* out_mean, double* out_m2, double* out_block_stats, float* out_walk_vals, uint64_t* out_steps,
@@ -953,8 +1004,10 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.dseg = scene->dseg; a.n_dseg = scene->n_dseg; a.nseg = scene->nseg; a.n_nseg = scene->n_nseg;
     a.F = DF;
     a.n_src = n_sources; a.srcs = d_srcs; a.src_support = d_sup;
+    if (n_sources > 0 && env_int("WOST_SOURCE_GRID", 1) && (rc = source_grid_for(scene, sources, n_sources, &a.sgrid))) return rc;
     if (alpha0) { alpha0_kernel<<<blocks_for(n_pts, 256), 256, 0, st>>>(a.F, s_pts.dev, n_pts, alpha0); CU(cudaGetLastError()); }
     a.pts = s_pts.dev; a.n_pts = n_pts; a.n_walks = W;
+    a.walks_magic = W <= 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / (unsigned long long)W);
     a.max_steps = P->max_steps; a.eps = P->eps; a.rmin = (float)((double)P->eps / 2.0);   // :167
     a.sp_mode = P->sp_mode; a.sigma_bar = P->sigma_bar;
     a.inv_sigma_bar = delta ? (float)(1.0 / (double)P->sigma_bar) : 0.0f;

@@ -8,6 +8,7 @@
 
 namespace wost {
 
+
 struct WalkArgs {
     const float4* dseg; int n_dseg;
     const float4* nseg; int n_nseg;
@@ -24,6 +25,7 @@ struct WalkArgs {
     unsigned long long* counter;           // next unassigned flat walk index
     unsigned long long* steps_total;
     int chunk;                             // walks a warp reserves per atomic
+    uint32_t walks_magic;                  // floor(2^32 / n_walks) (0xffffffff for n_walks = 1): flat walk index -> (point, walk)
     int lanes;                             // lanes of a warp that take walks (32; fewer for small jobs: walks that do not share
                                            // a warp do not wait for each other's divergent branches, see solve_impl)
     float ndisc_x, ndisc_y, ndisc_r, ndisc_r2;   // disc enclosing the Neumann polyline (inflated), for culling
@@ -35,11 +37,44 @@ struct WalkArgs {
     float phys_rcap;                       // physical mode with variable coefficients: step radius cap 1/sqrt(sigma_bar)
     MajorantPyramid maj;                   // ... or a spatially varying majorant (data == nullptr: sigma_bar everywhere)
     const float4* src_support;             // per source (cx, cy, R^2): exactly zero outside
+    SourceGrid sgrid;                      // which sources can be non-zero where (masks == nullptr: test every source's disc)
     int n_src; const DevField* srcs;       // shared-walk multi-source solve: n_src > 0 source fields (device array); per-walk
                                            // totals then form rows walk_vals[walk][n_src]
     long long n_trace; int trace_cap; float* trace; int* trace_len;
 };
 
+
+// Shared-walk solves evaluate MANY source terms per step, nearly all of them exactly zero at any one point (a DC-resistivity
+// source is a pair of narrow Gaussian blobs at two electrodes; each blob takes its exact-zero underflow shortcut beyond
+// sqrt(110 / q)).  The host bins the blobs' discs into a regular grid over their bounding box: per cell one bit per source that
+// can be non-zero anywhere in the cell (conservative: discs inflated by a cell), `outside` for points off the grid.  A step
+// then visits the set bits of ONE mask instead of testing every source.  Skipped sources contribute exactly nothing either
+// way, so every source's per-walk total keeps the bits of a single-source solve.
+
+// calls body(k) for every source k that may be non-zero at (x, y), in increasing k
+template <class Body>
+__device__ __forceinline__ void for_each_source(const WalkArgs& a, float x, float y, Body&& body) {
+    if (a.sgrid.masks) {
+        const float fx = (x - a.sgrid.x0) * a.sgrid.inv_dx, fy = (y - a.sgrid.y0) * a.sgrid.inv_dy;
+        long long cell = (long long)a.sgrid.nx * a.sgrid.ny;                           // the `outside` mask
+        if (fx >= 0.0f && fy >= 0.0f && fx < (float)a.sgrid.nx && fy < (float)a.sgrid.ny) cell = (long long)(int)fy * a.sgrid.nx + (int)fx;
+        const unsigned long long* m = a.sgrid.masks + cell * a.sgrid.words;
+        for (int w = 0; w < a.sgrid.words; ++w) {
+            unsigned long long bits = __ldg(m + w);
+            while (bits) {
+                const int k = w * 64 + __ffsll((long long)bits) - 1;
+                bits &= bits - 1ull;
+                body(k);
+            }
+        }
+    } else {
+        for (int k = 0; k < a.n_src; ++k) {
+            const float4 sup = __ldg(a.src_support + k);
+            if ((x - sup.x) * (x - sup.x) + (y - sup.y) * (y - sup.y) > sup.z) continue;   // exactly zero there
+            body(k);
+        }
+    }
+}
 
 // ---- field providers ---------------------------------------------------------------------------------------------------
 // The walk reads its fields through a provider FP: g, f, alpha (value and jet), sigma, sigma' table, sources of a
@@ -75,14 +110,15 @@ struct InterpFP {
 
 // sigma' (solvers/WoStSolver.py:88-127) in closed form through a provider: the arithmetic of sigma_prime_at (wost_device.cuh).
 // `alpha_xy`: alpha(x, y) if the caller has it already, a negative value otherwise.
+// `jet`: value / gradient / Laplacian of alpha at (x, y) if the caller has evaluated them already (WOST_SP_FULL), else nullptr.
 template <class FP>
-__device__ __forceinline__ float sigma_prime_fp(const WalkArgs& a, float x, float y, float alpha_xy) {
+__device__ __forceinline__ float sigma_prime_fp(const WalkArgs& a, float x, float y, float alpha_xy, const Jet* jet = nullptr) {
     const int mode = FP::sp_mode(a);
     if (mode == WOST_SP_FIELD) return FP::sigma_prime_field(a, x, y);
     const float sg = FP::has_sigma(a) ? FP::sigma(a, x, y) : 0.0f;
     if (mode == WOST_SP_RATIO) return div_z(sg, fmaxf(alpha_xy >= 0.0f ? alpha_xy : FP::alpha(a, x, y), 1e-8f));
     Jet j; j.v = 1.0f; j.gx = j.gy = j.l = 0.0f;
-    if (FP::has_alpha(a)) j = FP::alpha_jet(a, x, y);
+    if (FP::has_alpha(a)) j = jet ? *jet : FP::alpha_jet(a, x, y);
     if (j.v < 1e-8f) { j.v = 1e-8f; j.gx = j.gy = j.l = 0.0f; }
     const float ratio = div_z(sg, j.v);
     const float la = j.v + 1e-8f, lgx = div_z(j.gx, la), lgy = div_z(j.gy, la);
@@ -109,6 +145,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
     // [the fields' term tables].  The delta-tracking kernels' out-of-line field interpreter reads headers and terms from
     // here (wost_device.cuh, SM = true); the other kernels inline the interpreter and read the kernel parameters directly.
     constexpr bool SMF = FP::SMF;                      // the interpreter reads field tables from shared memory
+    constexpr bool TINY_NEU = NEU && !BIG && FP::N_NSEG >= 1 && FP::N_NSEG <= 2;   // scene-specialised kernels only
     if (SMF && FP::STAGE_FIELDS) {
         const int nf = FIELD_SOURCE0 + a.n_src;
         uint32_t* hdr = reinterpret_cast<uint32_t*>(smem);
@@ -185,9 +222,12 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
             if (mine && (unsigned long long)rank < avail) {
                 id = next + (unsigned long long)rank;
                 unsigned long long p, w;
-                if (total <= 0xffffffffull) {                          // the usual case: 32-bit division
-                    const uint32_t p32 = (uint32_t)id / (uint32_t)a.n_walks;
-                    p = p32; w = (uint32_t)id - p32 * (uint32_t)a.n_walks;
+                if (total <= 0xffffffffull) {                          // the usual case: 32 bits, division by multiplication
+                    // walks_magic = floor(2^32 / n_walks): the estimate is the quotient or one less (id < 2^32)
+                    uint32_t p32 = __umulhi((uint32_t)id, a.walks_magic);
+                    uint32_t w32 = (uint32_t)id - p32 * (uint32_t)a.n_walks;
+                    if (w32 >= (uint32_t)a.n_walks) { ++p32; w32 -= (uint32_t)a.n_walks; }
+                    p = p32; w = w32;
                 } else { p = id / (unsigned long long)a.n_walks; w = id - p * (unsigned long long)a.n_walks; }
                 pidx = (uint32_t)(a.point_index_base + (long long)p * a.point_index_stride); widx = (uint32_t)(a.walk_offset + (long long)w);
                 x = __ldg(a.pts + 2 * p); y = __ldg(a.pts + 2 * p + 1);
@@ -205,7 +245,11 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
         // no_instruction); one CTA barrier per iteration keeps the warps in the same code region: +5 % there, a loss
         // for the kernels with cooperative Neumann loops (iteration times differ per warp), so only there.
         bool none;
+#ifndef WOST_NO_LOCKSTEP
         if (!NEU && DELTA && !PHYS) none = !__syncthreads_or(active ? 1 : 0);
+#else
+        if (false) ;
+#endif
         else none = __ballot_sync(FULL, active) == 0u;
 
         // ---- boundary terms of the parked walks (:295-298), all parked lanes together ----------------------------------
@@ -321,11 +365,20 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 }
                 // the silhouette distance only matters if it can be smaller than dDirichlet (:212): every Neumann
                 // vertex is at least (|p - c| - R) away, so outside that margin min(dD, dN) = dD without looking.
+                if (TINY_NEU) {
+                    // a Neumann polyline of one or two segments (the DCR scenes' ground surface): testing every ray against it
+                    // with the exact arithmetic costs less than the cull + prefilter + the divergence they cause; one segment
+                    // has no interior vertex, hence no silhouette vertex (:64-81)
+                    want_sil = TRACE || n_nseg > 1;
+                    want_ray = true;
+                    if (PHYS) { const float gx = x - a.ndisc_x, gy = y - a.ndisc_y; gap = sqrtf(gx * gx + gy * gy) - a.ndisc_r; }
+                } else {
                 const float gx = x - a.ndisc_x, gy = y - a.ndisc_y;
                 const float g2 = gx * gx + gy * gy, lim = dD * 1.001f + a.ndisc_r;   // gap = sqrt(g2) - R > 1.001 dD, without the root
                 if (PHYS) gap = sqrtf(g2) - a.ndisc_r;
                 want_sil = TRACE || !(lim * lim < g2);
                 want_ray = ray_may_hit_disc(ox, oy, ex, ey, a.ndisc_x, a.ndisc_y, a.ndisc_r2);
+                }
                 // physical hits are limited to the star radius r <= max(dD, rmin): farther polylines cannot be hit
                 if (PHYS && gap > fmaxf(dD, a.rmin) + a.phys_nudge) want_ray = false;
             }
@@ -375,6 +428,14 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                         best_s = lane == src ? cs : best_s; best_k = lane == src ? ck : best_k;
                     }
                 } else if (want_ray) bvh_ray_cast<PHYS>(a.nseg, n_nseg, a.nbvh, a.bvh_slack, ox, oy, ex, ey, best_s, best_k);
+            } else if (TINY_NEU) {
+                if (want_ray) {
+#pragma unroll
+                    for (int k = 0; k < (FP::N_NSEG > 0 ? FP::N_NSEG : 1); ++k) {
+                        const float s = ray_segment_exact<PHYS>(nseg[2 * k], ox, oy, ex, ey);
+                        if (s < best_s) { best_s = s; best_k = k; }
+                    }
+                }
             } else if (ray_coop_max == 0 || __popc(need) > ray_coop_max) {
                 if (want_ray) ray_cast<PHYS>(nseg, n_nseg, ox, oy, ex, ey, best_s, best_k);
             } else if (small) {
@@ -457,12 +518,10 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 if (SRC && FP::MULTI && a.n_src > 0) {
                     if (vis) {
                         float* row = a.walk_vals + (size_t)id * a.n_src;
-                        for (int k = 0; k < a.n_src; ++k) {
-                            const float4 sup = __ldg(a.src_support + k);
-                            if ((yx - sup.x) * (yx - sup.x) + (yy - sup.y) * (yy - sup.y) > sup.z) continue;   // exactly zero there
+                        for_each_source(a, yx, yy, [&](int k) {
                             const float ck = FP::source(a, k, yx, yy) * wsrc;
                             if (ck != 0.0f) row[k] = row[k] + ck;
-                        }
+                        });
                     }
                 } else if (SRC) {
                     pc = vis ? FP::f(a, yx, yy) * wsrc : 0.0f;
@@ -523,10 +582,13 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
             }
 
             float sx = qx, sy = qy, gn = 0.0f, sbgn = 0.0f, alpha_s = 1.0f;
-            bool have_alpha_s = false;
+            bool have_alpha_s = false, edge = false;
+            Jet jet_s; jet_s.v = 1.0f; jet_s.gx = jet_s.gy = jet_s.l = 0.0f;
+            bool have_jet_s = false;
             if (DELTA && !PHYS) {
                 sbgn = interior_probability(a.iprob, r * a.sqrt_sigma_bar);                      // sigma_bar * |G^sb|(r)
                 gn = sbgn * a.inv_sigma_bar;                                            // screenedGreensNorm2D (utils.py:29-44)
+                edge = u24(o[1]) > sbgn;                                                // :271-272 (the draw does not depend on the sample)
             }
             if (!PHYS && (SRC || DELTA)) {                                              // :242 (Q10: also without a source)
                 float rho;
@@ -542,24 +604,36 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 const float rs = rho * r;                                               // utils.py:117
                 sx = x + rs * dx; sy = y + rs * dy;                                     // :245
                 float contrib = 0.0f;
-                if (norm2(sx - x, sy - y) > norm2(qx - x, qy - y)) {                    // :248-250
-                    sx = qx; sy = qy;
-                } else if (SRC) {
+                // :248-250 compares |sample - x| > |next - x| (two rounded norms).  sqrt is monotone, so a smaller-or-equal
+                // square decides "not greater", and a square larger by more than 2^-20 relative decides "greater" (the roots then
+                // differ by more than an ulp); only the sliver in between needs the roots themselves.
+                const float n2s = norm2_sq(sx - x, sy - y), n2q = norm2_sq(qx - x, qy - y);
+                bool beyond = n2s > n2q;
+                if (beyond && !(n2s > n2q * 1.000001f)) beyond = sqrtf(n2s) > sqrtf(n2q);
+                if (beyond) { sx = qx; sy = qy; }
+                // Delta tracking, interior lanes (the walker jumps to the sample point, :281-284): sigma' there needs value,
+                // gradient and Laplacian of alpha -- evaluated once, here; the value also serves the source term and the ratio.
+                if (DELTA && !edge && FP::sp_mode(a) == WOST_SP_FULL && FP::has_alpha(a)) {
+                    jet_s = FP::alpha_jet(a, sx, sy); have_jet_s = true;
+                    alpha_s = jet_s.v; have_alpha_s = true;
+                }
+                if (!beyond && SRC) {
                     if (FP::MULTI && a.n_src > 0) {
                         // shared walks: the path does not depend on f, so one walk serves every source; each source
                         // accumulates exactly the sum a single-source solve would (same expressions, same order)
                         float* row = a.walk_vals + (size_t)id * a.n_src;
                         float den = 1.0f;
-                        if (DELTA) { alpha_s = FP::alpha(a, sx, sy); have_alpha_s = true; den = sqrtf(alpha_s * alpha_x); }
+                        if (DELTA) {
+                            if (!have_alpha_s) { alpha_s = FP::alpha(a, sx, sy); have_alpha_s = true; }
+                            den = sqrtf(alpha_s * alpha_x);
+                        }
                         const float w4 = r * r / 4.0f;
-                        for (int k = 0; k < a.n_src; ++k) {
-                            const float4 sup = __ldg(a.src_support + k);
-                            if ((sx - sup.x) * (sx - sup.x) + (sy - sup.y) * (sy - sup.y) > sup.z) continue;   // exactly zero there
+                        for_each_source(a, sx, sy, [&](int k) {
                             const float fk = FP::source(a, k, sx, sy);
                             if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);   // fk != 0: plain division
-                        }
+                        });
                     } else if (DELTA) {                                                 // :252-254
-                        alpha_s = FP::alpha(a, sx, sy); have_alpha_s = true;
+                        if (!have_alpha_s) { alpha_s = FP::alpha(a, sx, sy); have_alpha_s = true; }
                         contrib = div_z(FP::f(a, sx, sy) * gn, sqrtf(alpha_s * alpha_x)) * atten;
                     } else
                         contrib = FP::f(a, sx, sy) * (r * r / 4.0f);       // :256
@@ -574,14 +648,13 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 // alpha(current_point) is the value computed when the walker arrived here (same function, same point).
                 // Both branches need alpha at their destination: evaluate it at ONE call site for all lanes (the edge
                 // branch at next_point, the interior branch at sample_point unless the source term already did).
-                const bool edge = u24(o[1]) > sbgn;
                 const float tx = edge ? qx : sx, ty = edge ? qy : sy;
                 const float alpha_t = (!edge && have_alpha_s) ? alpha_s : FP::alpha(a, tx, ty);
                 const float ratio = sqrtf(alpha_t / alpha_x);
                 if (edge) {
                     atten = atten * ratio;                                              // :277
                 } else {
-                    const float sp = sigma_prime_fp<FP>(a, sx, sy, alpha_t);   // :281 (alpha(sample) is alpha_t here)
+                    const float sp = sigma_prime_fp<FP>(a, sx, sy, alpha_t, have_jet_s ? &jet_s : nullptr);   // :281 (alpha(sample) is alpha_t here)
                     const float sc = fmaxf(1.0f - sp / a.sigma_bar, 0.0f);              // :282
                     atten = (atten * ratio) * sc;                                       // :283
                 }

@@ -1,12 +1,7 @@
 set -x
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2b_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2b_pytest_gpu.log
-# small-solve layout sweep
-for L in 32 0 1 2 4 8; do echo "== WOST_LANES_PER_WARP=$L"; WOST_LANES_PER_WARP=$L python tools/small_solve.py 100 2>&1 | grep '"jit": true\| on '; done > gpurun_out/r2b_small_sweep.txt 2>&1
-for S in 1 4; do echo "== auto, WOST_SMALL_WARPS_PER_SCHEDULER=$S"; WOST_SMALL_WARPS_PER_SCHEDULER=$S python tools/small_solve.py 100 2>&1 | grep ' on '; done >> gpurun_out/r2b_small_sweep.txt 2>&1
-# steps of the profiled passes (seed = pass index) and occupancy A/B
-for s in cfg5 cfg5_175e cfg4 cfg2 cfg1b cfg1a cfg3; do python tools/run_one.py $s 4; done > gpurun_out/r2b_run_one.txt 2>&1
-for mb in 4 5 6; do for s in cfg5 cfg4 cfg2 cfg1b; do echo -n "minblocks=$mb "; WOST_JIT_MIN_BLOCKS=$mb python tools/run_one.py $s 4 | tail -1; done; done > gpurun_out/r2b_minblocks.txt 2>&1
-for s in cfg5 cfg1a cfg3; do
-  timeout 600 ncu --set full --clock-control none -k regex:walk --launch-skip 2 -c 1 -f -o gpurun_out/r2_full_$s python tools/run_one.py $s 4 > gpurun_out/r2_ncu_full_$s.log 2>&1
-done
-ls gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2d_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2d_pytest_gpu.log
+bash tools/ab.sh "build/libwost_base.so build/libwost_new.so" cfg5 cfg5_175e cfg4 cfg2 cfg1b cfg1a cfg3 > gpurun_out/r2d_ab.txt 2>&1
+for rep in 1 2; do echo -n "lockstep "; WOST_LIB=build/libwost_new.so python tools/run_one.py cfg1b 4 | tail -1; echo -n "no-lockstep "; WOST_JIT_OPTS=-DWOST_NO_LOCKSTEP=1 WOST_LIB=build/libwost_new.so python tools/run_one.py cfg1b 4 | tail -1; done > gpurun_out/r2d_lockstep.txt 2>&1
+for L in build/libwost_base.so build/libwost_new.so; do echo "== $L"; WOST_LIB=$L python tools/survey_rank_job.py 16384; done > gpurun_out/r2d_survey_rank.txt 2>&1
+echo "== new, WOST_SOURCE_GRID=0" >> gpurun_out/r2d_survey_rank.txt; WOST_SOURCE_GRID=0 WOST_LIB=build/libwost_new.so python tools/survey_rank_job.py 16384 >> gpurun_out/r2d_survey_rank.txt 2>&1
+WOST_LIB=build/libwost_new.so python tools/survey_bench.py > gpurun_out/r2d_survey_bench.txt 2>&1
