@@ -846,8 +846,9 @@ int wost_sigma_prime_eval(const wost_fields_t* F, int32_t sp_mode, const float* 
 }  // extern "C"
 
 // Shared implementation of wost_solve (n_sources == 0: the source is fields->f) and wost_solve_multi_source.
-// Source grid of a shared-walk solve (SourceGrid, wost_walk.cuh): built once per (scene, source set) and kept with the scene.
-// Returns a grid with masks == nullptr when binning cannot help (no source with compact support).
+// Source grid of a shared-walk solve (SourceGrid, wost_device.cuh / for_each_source in wost_walk.cuh): built once per
+// (scene, source set) and kept with the scene.  Returns a grid with masks == nullptr when binning cannot help (no source
+// with compact support).
 static int source_grid_for(const wost_scene_t* scene, const wost_field_t* const* sources, int n, SourceGrid* out) {
     SourceGrid none{}; *out = none;
     std::vector<uint64_t> key(n);
@@ -857,38 +858,53 @@ static int source_grid_for(const wost_scene_t* scene, const wost_field_t* const*
     if (it != scene->source_grids.end()) { *out = it->second; return WOST_OK; }
     if (scene->source_grids.size() >= 64) return WOST_OK;               // bounded (grids live as long as the scene): test every disc instead
     // discs outside which each term is exactly zero (exp argument below -110: wost_device.cuh, term_value); a source without
-    // compact support is listed everywhere
-    struct Disc { int k; double x, y, r; };
+    // compact support is listed everywhere.  Blob mode: every source is a plain sum of bare Gaussians.
+    struct Disc { int bit; double x, y, r; };
     std::vector<Disc> discs; std::vector<char> everywhere(n, 0);
+    std::vector<float4> blobs; std::vector<int> blob_src;
+    bool blob_mode = env_int("WOST_SOURCE_BLOBS", 1) != 0;
     double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
     for (int k = 0; k < n; ++k) {
-        if (!(sources[k]->support.z < 1.0e38f)) { everywhere[k] = 1; continue; }
-        for (const wost_term_t& t : sources[k]->h_terms) {
+        const wost_field* f = sources[k];
+        if (!(f->support.z < 1.0e38f)) { everywhere[k] = 1; blob_mode = false; continue; }
+        if (f->d.mask_kind != WOST_MASK_NONE || f->d.c0 != 0.0f) blob_mode = false;
+        for (const wost_term_t& t : f->h_terms) {
+            if (t.kind != WOST_TERM_PRODUCT || t.px || t.py || t.t1 != WOST_TRIG_NONE || t.t2 != WOST_TRIG_NONE) blob_mode = false;
             const double r = std::sqrt(112.0 / (double)t.q) * 1.001 + 1e-6;
             discs.push_back({k, t.cx, t.cy, r});
+            blobs.push_back(make_float4(t.A, t.q, t.cx, t.cy)); blob_src.push_back(k);
             x0 = std::min(x0, t.cx - r); x1 = std::max(x1, t.cx + r); y0 = std::min(y0, t.cy - r); y1 = std::max(y1, t.cy + r);
         }
     }
     if (discs.empty()) { scene->source_grids[key] = none; return WOST_OK; }
+    if (blob_mode) for (size_t b = 0; b < discs.size(); ++b) discs[b].bit = (int)b;   // one bit per blob instead of per source
+    const int n_bits = blob_mode ? (int)discs.size() : n;
     SourceGrid g{};
-    g.nx = 64; g.ny = 64; g.words = (n + 63) / 64;
+    g.nx = 64; g.ny = 64; g.words = (n_bits + 63) / 64;
     const double dx = std::max((x1 - x0) / g.nx, 1e-30), dy = std::max((y1 - y0) / g.ny, 1e-30);
     g.x0 = (float)x0; g.y0 = (float)y0; g.inv_dx = (float)(1.0 / dx); g.inv_dy = (float)(1.0 / dy);
     std::vector<unsigned long long> m(((size_t)g.nx * g.ny + 1) * g.words, 0ull);
-    auto set = [&](size_t cell, int k) { m[cell * g.words + k / 64] |= 1ull << (k % 64); };
-    for (int k = 0; k < n; ++k) if (everywhere[k]) for (size_t c = 0; c <= (size_t)g.nx * g.ny; ++c) set(c, k);
+    auto set = [&](size_t cell, int bit) { m[cell * g.words + bit / 64] |= 1ull << (bit % 64); };
+    if (!blob_mode) for (int k = 0; k < n; ++k) if (everywhere[k]) for (size_t c = 0; c <= (size_t)g.nx * g.ny; ++c) set(c, k);
     for (const Disc& d : discs) {                                       // the disc's box plus one cell all round (fp32 cell lookup)
         const int i0 = std::max(0, (int)std::floor((d.x - d.r - x0) / dx) - 1), i1 = std::min(g.nx - 1, (int)std::floor((d.x + d.r - x0) / dx) + 1);
         const int j0 = std::max(0, (int)std::floor((d.y - d.r - y0) / dy) - 1), j1 = std::min(g.ny - 1, (int)std::floor((d.y + d.r - y0) / dy) + 1);
-        for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) set((size_t)j * g.nx + i, d.k);
+        for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) set((size_t)j * g.nx + i, d.bit);
     }
-    unsigned long long* dm = nullptr;
-    if (cudaMalloc((void**)&dm, m.size() * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemcpy(dm, m.data(), m.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice) != cudaSuccess) {
+    // one allocation: masks | blobs | blob -> source
+    const size_t mask_bytes = (m.size() * sizeof(unsigned long long) + 15) / 16 * 16, blob_bytes = blob_mode ? blobs.size() * sizeof(float4) : 0,
+                 src_bytes = blob_mode ? blob_src.size() * sizeof(int) : 0;
+    char* dm = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dm, mask_bytes + blob_bytes + src_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(dm, m.data(), m.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && blob_mode) e = cudaMemcpy(dm + mask_bytes, blobs.data(), blob_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && blob_mode) e = cudaMemcpy(dm + mask_bytes + blob_bytes, blob_src.data(), src_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
         cudaGetLastError(); cudaFree(dm);
         return fail(WOST_ERR_ALLOC, "source grid: device allocation failed");
     }
-    g.masks = dm;
+    g.masks = reinterpret_cast<const unsigned long long*>(dm);
+    if (blob_mode) { g.blobs = reinterpret_cast<const float4*>(dm + mask_bytes); g.blob_src = reinterpret_cast<const int*>(dm + mask_bytes + blob_bytes); }
     scene->source_grids[key] = g;
     *out = g;
     return WOST_OK;
@@ -1015,6 +1031,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
     a.icdf = s_icdf.dev; a.icdf_len = P->icdf_len;
     if (delta && !phys_delta && !(a.iprob = iprob_table(scene->device))) return fail(WOST_ERR_ALLOC, "interior-probability table: device allocation failed");
     a.key0 = (uint32_t)P->seed; a.key1 = (uint32_t)(P->seed >> 32);
+    for (int r = 0; r < 10; ++r) { a.ks[2 * r] = a.key0 + (uint32_t)r * 0x9E3779B9u; a.ks[2 * r + 1] = a.key1 + (uint32_t)r * 0xBB67AE85u; }
     a.point_index_base = P->point_index_base; a.point_index_stride = pstride; a.walk_offset = P->walk_offset;
     a.walk_vals = vals; a.counter = ctrs; a.steps_total = ctrs + 1;
     a.ndisc_x = scene->ndisc_x; a.ndisc_y = scene->ndisc_y; a.ndisc_r = scene->ndisc_r; a.ndisc_r2 = scene->ndisc_r2;

@@ -20,7 +20,8 @@ struct WalkArgs {
     int sp_mode; float sigma_bar, inv_sigma_bar, sqrt_sigma_bar;
     const float* icdf; int icdf_len;
     const float* iprob;                    // 1 - 1/I0(z) on [0, 21]: the table of include/wost_math.h (delta tracking)
-    uint32_t key0, key1; long long point_index_base, point_index_stride, walk_offset;   // global index of point p: base + p * stride
+    uint32_t key0, key1; uint32_t ks[20];  // Philox key and its ten round keys
+    long long point_index_base, point_index_stride, walk_offset;   // global index of point p: base + p * stride
     float* walk_vals;
     unsigned long long* counter;           // next unassigned flat walk index
     unsigned long long* steps_total;
@@ -51,27 +52,47 @@ struct WalkArgs {
 // then visits the set bits of ONE mask instead of testing every source.  Skipped sources contribute exactly nothing either
 // way, so every source's per-walk total keeps the bits of a single-source solve.
 
-// calls body(k) for every source k that may be non-zero at (x, y), in increasing k
-template <class Body>
+// calls body(k, f_k(x, y)) for every source k that may be non-zero at (x, y), in increasing k
+template <class FP, class Body>
 __device__ __forceinline__ void for_each_source(const WalkArgs& a, float x, float y, Body&& body) {
     if (a.sgrid.masks) {
         const float fx = (x - a.sgrid.x0) * a.sgrid.inv_dx, fy = (y - a.sgrid.y0) * a.sgrid.inv_dy;
         long long cell = (long long)a.sgrid.nx * a.sgrid.ny;                           // the `outside` mask
         if (fx >= 0.0f && fy >= 0.0f && fx < (float)a.sgrid.nx && fy < (float)a.sgrid.ny) cell = (long long)(int)fy * a.sgrid.nx + (int)fx;
         const unsigned long long* m = a.sgrid.masks + cell * a.sgrid.words;
+        if (a.sgrid.blobs) {
+            // Blob mode.  f_k = ((0 + t_0) + t_1) + ... in term order (field_eval_inl); a blob that is not listed here is
+            // beyond its exact-zero radius and would add +-0, which changes nothing unless the whole sum is zero -- and a zero
+            // sum is skipped by the caller either way.  Each listed blob: the arithmetic of term_value for a bare Gaussian.
+            int cur = -1; float acc = 0.0f;
+            for (int w = 0; w < a.sgrid.words; ++w) {
+                unsigned long long bits = __ldg(m + w);
+                while (bits) {
+                    const int b = w * 64 + __ffsll((long long)bits) - 1;
+                    bits &= bits - 1ull;
+                    const int k = __ldg(a.sgrid.blob_src + b);
+                    if (k != cur) { if (cur >= 0) body(cur, acc); cur = k; acc = 0.0f; }
+                    const float4 g = __ldg(a.sgrid.blobs + b);                          // A, q, cx, cy
+                    const float ddx = x - g.z, ddy = y - g.w, e = -g.y * (ddx * ddx + ddy * ddy);
+                    acc += e < -110.0f ? g.x * 0.0f * 1.0f : g.x * wm_expf(e);
+                }
+            }
+            if (cur >= 0) body(cur, acc);
+            return;
+        }
         for (int w = 0; w < a.sgrid.words; ++w) {
             unsigned long long bits = __ldg(m + w);
             while (bits) {
                 const int k = w * 64 + __ffsll((long long)bits) - 1;
                 bits &= bits - 1ull;
-                body(k);
+                body(k, FP::source(a, k, x, y));
             }
         }
     } else {
         for (int k = 0; k < a.n_src; ++k) {
             const float4 sup = __ldg(a.src_support + k);
             if ((x - sup.x) * (x - sup.x) + (y - sup.y) * (y - sup.y) > sup.z) continue;   // exactly zero there
-            body(k);
+            body(k, FP::source(a, k, x, y));
         }
     }
 }
@@ -334,15 +355,15 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                                   : dirichlet_distance(dseg, n_dseg, x, y, nullptr);      // :208
             uint32_t w0;
             if (PHYS) {
-                philox4x32_10(pidx, widx, (uint32_t)steps, 2u, a.key0, a.key1, o);      // stream tag 2: physical mode
+                philox4x32_10_ks(pidx, widx, (uint32_t)steps, 2u, a.ks, o);      // stream tag 2: physical mode
                 w0 = o[0];
             } else if (!SRC && !DELTA) {
                 // Laplace walks use one 32-bit word per step: one Philox block (stream tag 1) serves four steps
                 const int sel = steps & 3;
-                if (sel == 0) philox4x32_10(pidx, widx, (uint32_t)steps >> 2, 1u, a.key0, a.key1, o);
+                if (sel == 0) philox4x32_10_ks(pidx, widx, (uint32_t)steps >> 2, 1u, a.ks, o);
                 w0 = sel == 0 ? o[0] : (sel == 1 ? o[1] : (sel == 2 ? o[2] : o[3]));
             } else {
-                philox4x32_10(pidx, widx, (uint32_t)steps, 0u, a.key0, a.key1, o);
+                philox4x32_10_ks(pidx, widx, (uint32_t)steps, 0u, a.ks, o);
                 w0 = o[0];
             }
             float theta;
@@ -518,8 +539,8 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 if (SRC && FP::MULTI && a.n_src > 0) {
                     if (vis) {
                         float* row = a.walk_vals + (size_t)id * a.n_src;
-                        for_each_source(a, yx, yy, [&](int k) {
-                            const float ck = FP::source(a, k, yx, yy) * wsrc;
+                        for_each_source<FP>(a, yx, yy, [&](int k, float fk) {
+                            const float ck = fk * wsrc;
                             if (ck != 0.0f) row[k] = row[k] + ck;
                         });
                     }
@@ -536,7 +557,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
             bool pd_vol = false;
             if (PHYS && DELTA) {
                 uint32_t o2[4];
-                philox4x32_10(pidx, widx, (uint32_t)steps, 3u, a.key0, a.key1, o2);     // stream tag 3: branch choice
+                philox4x32_10_ks(pidx, widx, (uint32_t)steps, 3u, a.ks, o2);     // stream tag 3: branch choice
                 pd_vol = u24(o2[0]) < pd_m1 / pd_i0c;
             }
             if (NEU) {
@@ -611,11 +632,13 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 bool beyond = n2s > n2q;
                 if (beyond && !(n2s > n2q * 1.000001f)) beyond = sqrtf(n2s) > sqrtf(n2q);
                 if (beyond) { sx = qx; sy = qy; }
-                // Delta tracking, interior lanes (the walker jumps to the sample point, :281-284): sigma' there needs value,
-                // gradient and Laplacian of alpha -- evaluated once, here; the value also serves the source term and the ratio.
-                if (DELTA && !edge && FP::sp_mode(a) == WOST_SP_FULL && FP::has_alpha(a)) {
-                    jet_s = FP::alpha_jet(a, sx, sy); have_jet_s = true;
-                    alpha_s = jet_s.v; have_alpha_s = true;
+                // Delta tracking with the closed-form sigma' (WOST_SP_FULL): the walker's destination is the sample point on
+                // interior steps (:281-284, where sigma' needs value, gradient and Laplacian of alpha) and next_point on edge
+                // steps (:277, value only).  ONE evaluation site for all lanes: the jet at the destination.  Its value also serves
+                // the source term of interior lanes; the few edge lanes evaluate alpha at their sample point separately.
+                if (DELTA && FP::sp_mode(a) == WOST_SP_FULL && FP::has_alpha(a)) {
+                    jet_s = FP::alpha_jet(a, edge ? qx : sx, edge ? qy : sy); have_jet_s = true;
+                    if (!edge) { alpha_s = jet_s.v; have_alpha_s = true; }
                 }
                 if (!beyond && SRC) {
                     if (FP::MULTI && a.n_src > 0) {
@@ -628,8 +651,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                             den = sqrtf(alpha_s * alpha_x);
                         }
                         const float w4 = r * r / 4.0f;
-                        for_each_source(a, sx, sy, [&](int k) {
-                            const float fk = FP::source(a, k, sx, sy);
+                        for_each_source<FP>(a, sx, sy, [&](int k, float fk) {
                             if (fk != 0.0f) row[k] = row[k] + (DELTA ? (fk * gn / den) * atten : fk * w4);   // fk != 0: plain division
                         });
                     } else if (DELTA) {                                                 // :252-254
@@ -649,7 +671,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 // Both branches need alpha at their destination: evaluate it at ONE call site for all lanes (the edge
                 // branch at next_point, the interior branch at sample_point unless the source term already did).
                 const float tx = edge ? qx : sx, ty = edge ? qy : sy;
-                const float alpha_t = (!edge && have_alpha_s) ? alpha_s : FP::alpha(a, tx, ty);
+                const float alpha_t = have_jet_s ? jet_s.v : ((!edge && have_alpha_s) ? alpha_s : FP::alpha(a, tx, ty));
                 const float ratio = sqrtf(alpha_t / alpha_x);
                 if (edge) {
                     atten = atten * ratio;                                              // :277

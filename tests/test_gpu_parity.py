@@ -778,11 +778,16 @@ def test_shared_walk_multi_source_equals_single_source_solves():
         fs = [TermField.constant(-4.0), TermField.polynomial({(1, 0): 1.0, (0, 2): 2.0}), TermField.gaussian_sum([(3.0, (1.0, 1.0), 4.0)])]
         sol = WostSolver_2D(PolyLinesSimple(s2.dirichlet), s2.g, PolyLinesSimple(s2.neumann), source=fs[0], compat=compat)
         pts = s2.points[::25].contiguous()
-        m = sol.solve_multi_source(pts, fs, 1500, s2.max_steps, s2.eps, seed=3)
-        for k, f in enumerate(fs):
-            sol.setSourceTerm(f)
-            o = sol.solve_raw(pts, 1500, s2.max_steps, s2.eps, seed=3)
-            assert np.array_equal(m["mean"][k], o["mean"]) and np.array_equal(m["m2"][k], o["m2"]), (compat, k)
+        # sources without compact support are listed in every cell of the source grid; a set made of Gaussian blobs only
+        # (overlapping, narrow and wide, one blob far outside the domain) takes the per-blob path
+        blobs = [TermField.gaussian_sum([(3.0, (1.0, 1.0), 4.0)]), TermField.gaussian_sum([(2.0, (-1.0, 0.5), 30.0), (-1.5, (1.2, -0.7), 600.0)]),
+                 TermField.gaussian_sum([(1.0, (0.9, 1.1), 80.0), (0.5, (25.0, 3.0), 50.0), (-2.0, (-1.5, -1.5), 200.0)])]
+        for sources in (fs, blobs):
+            m = sol.solve_multi_source(pts, sources, 1500, s2.max_steps, s2.eps, seed=3)
+            for k, f in enumerate(sources):
+                sol.setSourceTerm(f)
+                o = sol.solve_raw(pts, 1500, s2.max_steps, s2.eps, seed=3)
+                assert np.array_equal(m["mean"][k], o["mean"]) and np.array_equal(m["m2"][k], o["m2"]), (compat, k)
     # bounded scratch: passes over the points do not change anything
     import os
     os.environ["WOST_MAX_WALK_VALS"] = str(2 * 2500 * 5)
