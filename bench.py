@@ -322,7 +322,7 @@ def strong_scaling(torch, dist, dist_mod, quick):
     c5 = sc.cfg5(ELECTRODES)
     srcs = [DipoleSource((-38.0 + 1.1 * k, 0.0), (38.0 - 1.1 * k, 0.0)) for k in range(64)]
     survey = DCRSurvey(PolyLinesSimple(c5.dirichlet), PolyLinesSimple(c5.neumann), c5.alpha, c5.points, srcs, sink_sign=+1.0)
-    Ws = 4096 if quick else 16384
+    Ws = 4096 if quick else 65536                                         # >= 1.4 M walks per GPU at N = 8: the tail of the longest walks stays small
     res = None
     for i in range(2):
         survey.run(nWalks=Ws, maxSteps=c5.max_steps, eps=c5.eps, seed=99, shared_walks=True)

@@ -1,5 +1,8 @@
 set -x
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2f_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2f_pytest_gpu.log
-bash tools/ab.sh "build/libwost_v10.so build/libwost_v12.so" cfg5 cfg5_175e cfg4 cfg2 cfg1b cfg1a cfg3 > gpurun_out/r2f_ab.txt 2>&1
-for L in build/libwost_v10.so build/libwost_v12.so; do echo "== $L"; WOST_LIB=$L python tools/survey_rank_job.py 16384; done > gpurun_out/r2f_survey_rank.txt 2>&1
-echo "== v12, WOST_SOURCE_BLOBS=0" >> gpurun_out/r2f_survey_rank.txt; WOST_SOURCE_BLOBS=0 WOST_LIB=build/libwost_v12.so python tools/survey_rank_job.py 16384 >> gpurun_out/r2f_survey_rank.txt 2>&1
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2g_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2g_pytest_gpu.log
+( time timeout 900 python bench.py ) > gpurun_out/r2g_bench1.json 2> gpurun_out/r2g_bench1.err; echo rc=$?; tail -c 300 gpurun_out/r2g_bench1.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2g_launches.csv python bench.py --headline-only --steps 2 --warmup 3 > gpurun_out/r2g_ncu_launches.log 2>&1
+for s in cfg5 cfg4 cfg2 cfg1b cfg1a cfg3; do
+  timeout 600 ncu --set full --clock-control none -k regex:walk --launch-skip 2 -c 1 -f -o gpurun_out/r2g_full_$s python tools/run_one.py $s 4 > gpurun_out/r2g_ncu_full_$s.log 2>&1
+done
+python tools/small_solve.py 200 2>&1 | grep ' on ' > gpurun_out/r2g_small.txt
