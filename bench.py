@@ -287,7 +287,8 @@ def rmse_sweep(torch, dist_mod, key, walks_list):
     out = []
     dist_mod.solve_sharded(solver, s.points, 64, s.max_steps, s.eps, seed=1)["mean"].cpu()           # warm-up
     for W in walks_list:
-        dist_mod.solve_sharded(solver, s.points, W, s.max_steps, s.eps, seed=7)["mean"].cpu()       # shape warm-up (buffers, kernel)
+        for i in range(2):                                                  # shape warm-up (scratch buffers, specialised kernel)
+            dist_mod.solve_sharded(solver, s.points, W, s.max_steps, s.eps, seed=7 + i)["mean"].cpu()
         torch.cuda.synchronize(); t0 = time.perf_counter()
         r = dist_mod.solve_sharded(solver, s.points, W, s.max_steps, s.eps, seed=1000 + W)
         mean = r["mean"].cpu()

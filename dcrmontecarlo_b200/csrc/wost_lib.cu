@@ -39,20 +39,17 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct Arena {
     struct Block { char* p; size_t cap, off; };
     std::vector<Block> blocks;
-    void reset() {                                       // start of a call: everything is free again
-        if (blocks.size() > 1) {                         // the previous call outgrew its block: one block of the total size
-            size_t tot = 0;
-            for (auto& b : blocks) { tot += b.cap; cudaFree(b.p); }   // cudaFree waits for the device: nothing is in use
-            blocks.clear();
-            char* p = nullptr;
-            if (cudaMalloc((void**)&p, tot) == cudaSuccess) blocks.push_back({p, tot, 0}); else cudaGetLastError();
-        }
-        for (auto& b : blocks) b.off = 0;
-    }
+    void reset() { for (auto& b : blocks) b.off = 0; }   // start of a call: everything is free again
+    // Bytes come from the newest block only.  A call that outgrows it gets a block sized for the whole call next time (twice
+    // what is held so far, at most 256 MiB extra); the outgrown blocks stay allocated until wost_scene_trim / _destroy --
+    // freeing or merging them here would synchronise with the device (cudaFree) in the middle of a stream of solves: round 1's
+    // merge on the NEXT call cost that call ~1 ms, which is what a sweep over growing job sizes then measured.
     void* take(size_t bytes) {
         bytes = (bytes + 255) & ~(size_t)255;
         if (!blocks.empty()) { Block& b = blocks.back(); if (b.off + bytes <= b.cap) { void* r = b.p + b.off; b.off += bytes; return r; } }
-        const size_t cap = std::max(bytes + (bytes >> 2), (size_t)1 << 20);
+        size_t held = 0;
+        for (auto& b : blocks) held += b.cap;
+        const size_t cap = std::max(std::max(bytes + (bytes >> 2), std::min(2 * held, held + ((size_t)256 << 20))), (size_t)1 << 20);
         char* p = nullptr;
         if (cudaMalloc((void**)&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         blocks.push_back({p, cap, bytes});

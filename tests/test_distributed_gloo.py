@@ -104,6 +104,11 @@ def test_shard_plan_covers_everything_once():
             assert max(work) <= 1.07 * (P * W / world) + WALK_BLOCK * P, (P, W, world, work)
     assert all(sh.w0 == 0 and sh.w1 == 150 for sh in shard_plan(404, 150, 8))          # many points: by points
     assert not all(sh.w1 == 4096 for sh in shard_plan(3, 4096, 2))                     # 3 points on 2 ranks: by walks (2 blocks each)
+    # the headline job: 175 electrodes on 8 ranks split 22 / 21 (0.6 % above the even share) -- by points, although the
+    # 2 048 walk blocks would divide evenly: the point-sharded gather is 24 bytes per point and needs no merge
+    plan = shard_plan(175, 8 * 32768, 8)
+    assert all(sh.w0 == 0 and sh.w1 == 8 * 32768 for sh in plan) and sorted(sh.n_points for sh in plan) == [21] + [22] * 7
+    assert not all(sh.w1 == 16384 for sh in shard_plan(9, 16384, 8))                   # 9 electrodes on 8 ranks: by walks (2 blocks each)
 
 
 # ---- DCRSurvey.run: electrode sharding (shared walks) and source sharding over ranks ---------------------------------

@@ -1,8 +1,7 @@
 set -x
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2g_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2g_pytest_gpu.log
-( time timeout 900 python bench.py ) > gpurun_out/r2g_bench1.json 2> gpurun_out/r2g_bench1.err; echo rc=$?; tail -c 300 gpurun_out/r2g_bench1.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2g_launches.csv python bench.py --headline-only --steps 2 --warmup 3 > gpurun_out/r2g_ncu_launches.log 2>&1
-for s in cfg5 cfg4 cfg2 cfg1b cfg1a cfg3; do
-  timeout 600 ncu --set full --clock-control none -k regex:walk --launch-skip 2 -c 1 -f -o gpurun_out/r2g_full_$s python tools/run_one.py $s 4 > gpurun_out/r2g_ncu_full_$s.log 2>&1
+nvidia-smi -L | head -8 > gpurun_out/r2_multi_smi.txt
+( time timeout 600 python -m pytest tests/test_gpu_multi.py -x -q ) > gpurun_out/r2_pytest_multi.log 2>&1; tail -n 4 gpurun_out/r2_pytest_multi.log
+for N in 8 2; do
+  ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 ) > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo rc=$?; tail -c 400 gpurun_out/r2_bench_n$N.err
 done
-python tools/small_solve.py 200 2>&1 | grep ' on ' > gpurun_out/r2g_small.txt
+( time timeout 600 python bench.py ) > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
