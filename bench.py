@@ -400,16 +400,28 @@ def main():
     jit_used = nat.jit_last_note() == ""
     sampler = ClockSampler(local); sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     outs = []
     ev0.record()
     for it in range(args.steps):
         outs.append(step_resident(args.warmup + it))
+        marks[it].record()                                               # per-step times (diagnostic; the figure is ev0 -> ev1)
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
+    each = torch.tensor([(ev0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(each, op=dist.ReduceOp.MAX)
+    each_ms = [round(float(v), 4) for v in each.tolist()]
     tot_steps = int(sum(int(o["steps"]) for o in outs))                   # already the sum over all ranks (it travels in the gather)
     head_checksum = dm.checksum(outs[-1]["mean"])
     clocks = sampler.stop()                                              # the clocks belong to the device-timed region
+    if dist is not None:                                                 # every rank samples its own GPU: report the slowest, all reasons
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        mhz = [c["sm_mhz"] for c in allc if c["sm_mhz"] is not None]
+        clocks = dict(clocks, sm_mhz=min(mhz) if mhz else None, sm_mhz_per_rank=[c["sm_mhz"] for c in allc],
+                      reasons=sorted(set().union(*[set(c["reasons"]) for c in allc])))
     shard = outs[-1]["shard"]
 
     # ---- end to end: host buffers -----------------------------------------------------------------------------------------
@@ -434,7 +446,8 @@ def main():
     if args.headline_only:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": tot_steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms / args.steps, "specialised_kernel": jit_used}), flush=True)
+                              "ms_per_step": ms / args.steps, "ms_each_step_max_over_ranks": each_ms, "specialised_kernel": jit_used,
+                              "e2e_ms_per_step": e2e_ms / args.steps, "clocks": clocks}), flush=True)
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
         return
@@ -455,8 +468,8 @@ def main():
         n_launch = launches_per_solve(s)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
+            "ms_per_step": ms / args.steps, "ms_each_step_max_over_ranks": each_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "electrodes": ELECTRODES, "walks_per_electrode": Wg, "walks_per_electrode_per_gpu": WALKS,
                        "walk_steps_per_step": tot_steps / args.steps,
                        "l2_note": "every step uses a fresh Philox key and rewrites its per-walk totals (%d MiB per GPU); the working set is registers / shared memory, not L2" % (ELECTRODES * WALKS * 4 >> 20),

@@ -1,7 +1,5 @@
 set -x
-nvidia-smi -L | head -8 > gpurun_out/r2_multi_smi.txt
-( time timeout 600 python -m pytest tests/test_gpu_multi.py -x -q ) > gpurun_out/r2_pytest_multi.log 2>&1; tail -n 4 gpurun_out/r2_pytest_multi.log
-for N in 8 2; do
-  ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 ) > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo rc=$?; tail -c 400 gpurun_out/r2_bench_n$N.err
+for W in 3 40; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2952$((W%10)) bench.py --gpus 8 --steps 10 --warmup $W --headline-only > gpurun_out/r2_n8_headline_w$W.json 2> gpurun_out/r2_n8_headline_w$W.err; echo rc=$?
 done
-( time timeout 600 python bench.py ) > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 40 --warmup 3 --headline-only > gpurun_out/r2_n8_headline_k40.json 2> gpurun_out/r2_n8_headline_k40.err; echo rc=$?
