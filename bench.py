@@ -396,9 +396,10 @@ def main():
 
     for it in range(args.warmup):
         step_resident(it)
-    sync_all()
     jit_used = nat.jit_last_note() == ""
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local)                                        # nvmlInit BEFORE the barrier: it takes milliseconds, differently on
+    sync_all()                                                           # every rank, and the first gather would wait for the last rank to start
+    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     outs = []
