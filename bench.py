@@ -210,11 +210,13 @@ def tile_points(points, n):
     return points.repeat(reps, 1)[:n].contiguous()
 
 
-def time_solves(torch, fn, reps, warm):
+def time_solves(torch, fn, reps, warm, dist=None):
     """CUDA-event time of `reps` back-to-back calls of fn(i) on the current stream after `warm` warm-ups (ms)."""
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
+    if dist is not None:                                                 # collective callers: all ranks start together
+        dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     outs = [fn(warm + i) for i in range(reps)]
@@ -310,7 +312,7 @@ def strong_scaling(torch, dist, dist_mod, quick):
     solver = s.make_solver()
     W = 153600 if quick else 614400
     reps = 3
-    ms, outs = time_solves(torch, lambda i: dist_mod.solve_sharded(solver, s.points, W, s.max_steps, s.eps, seed=4242), reps, 2)
+    ms, outs = time_solves(torch, lambda i: dist_mod.solve_sharded(solver, s.points, W, s.max_steps, s.eps, seed=4242), reps, 2, dist)
     t = torch.tensor([ms / reps], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -886,7 +886,13 @@ static int source_grid_for(const wost_scene_t* scene, const wost_field_t* const*
     for (const Disc& d : discs) {                                       // the disc's box plus one cell all round (fp32 cell lookup)
         const int i0 = std::max(0, (int)std::floor((d.x - d.r - x0) / dx) - 1), i1 = std::min(g.nx - 1, (int)std::floor((d.x + d.r - x0) / dx) + 1);
         const int j0 = std::max(0, (int)std::floor((d.y - d.r - y0) / dy) - 1), j1 = std::min(g.ny - 1, (int)std::floor((d.y + d.r - y0) / dy) + 1);
-        for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) set((size_t)j * g.nx + i, d.bit);
+        for (int j = j0; j <= j1; ++j)
+            for (int i = i0; i <= i1; ++i) {
+                // cell rectangle grown by one cell on every side against the disc itself (not its box: a fifth fewer entries)
+                const double cx0 = x0 + (i - 1) * dx, cx1 = x0 + (i + 2) * dx, cy0 = y0 + (j - 1) * dy, cy1 = y0 + (j + 2) * dy;
+                const double qx = std::min(std::max(d.x, cx0), cx1) - d.x, qy = std::min(std::max(d.y, cy0), cy1) - d.y;
+                if (qx * qx + qy * qy <= d.r * d.r) set((size_t)j * g.nx + i, d.bit);
+            }
     }
     // one allocation: masks | blobs | blob -> source
     const size_t mask_bytes = (m.size() * sizeof(unsigned long long) + 15) / 16 * 16, blob_bytes = blob_mode ? blobs.size() * sizeof(float4) : 0,

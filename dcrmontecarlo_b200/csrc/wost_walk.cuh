@@ -262,15 +262,12 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
             next += cnt < avail ? cnt : avail;
             need = __ballot_sync(FULL, !active && !retired);
         }
-        // Dirichlet-only delta-tracking kernels are instruction-fetch bound (ncu: a third of the stall samples are
-        // no_instruction); one CTA barrier per iteration keeps the warps in the same code region: +5 % there, a loss
-        // for the kernels with cooperative Neumann loops (iteration times differ per warp), so only there.
+        // Dirichlet-only delta-tracking kernels: one CTA barrier per iteration keeps the warps in the same code region.  With the
+        // interpreter (static kernels, instruction-fetch bound) that is +5 %; with the specialised kernels it is within noise
+        // (1.49 vs 1.43 / 1.52 vs 1.56 ms on cfg 1b).  For the kernels with cooperative Neumann loops it is a loss
+        // (iteration times differ per warp), so only here.
         bool none;
-#ifndef WOST_NO_LOCKSTEP
         if (!NEU && DELTA && !PHYS) none = !__syncthreads_or(active ? 1 : 0);
-#else
-        if (false) ;
-#endif
         else none = __ballot_sync(FULL, active) == 0u;
 
         // ---- boundary terms of the parked walks (:295-298), all parked lanes together ----------------------------------

@@ -1,5 +1,7 @@
 set -x
-for W in 3 40; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2952$((W%10)) bench.py --gpus 8 --steps 10 --warmup $W --headline-only > gpurun_out/r2_n8_headline_w$W.json 2> gpurun_out/r2_n8_headline_w$W.err; echo rc=$?
-done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 40 --warmup 3 --headline-only > gpurun_out/r2_n8_headline_k40.json 2> gpurun_out/r2_n8_headline_k40.err; echo rc=$?
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2i_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2i_pytest_gpu.log
+( time WOST_JIT=1 timeout 900 python -m pytest tests -m gpu -q -k "not jit" ) > gpurun_out/r2i_pytest_gpu_jit1.log 2>&1; tail -n 3 gpurun_out/r2i_pytest_gpu_jit1.log
+( time WOST_JIT=0 timeout 900 python -m pytest tests -m gpu -q -k "not jit" ) > gpurun_out/r2i_pytest_gpu_jit0.log 2>&1; tail -n 3 gpurun_out/r2i_pytest_gpu_jit0.log
+( time timeout 900 python bench.py ) > gpurun_out/r2i_bench1.json 2> gpurun_out/r2i_bench1.err; echo rc=$?; tail -c 300 gpurun_out/r2i_bench1.err
+python tools/survey_rank_job.py 16384 > gpurun_out/r2i_survey_rank.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2i_smoke.txt 2>&1; tail -2 gpurun_out/r2i_smoke.txt
