@@ -60,6 +60,7 @@ EXPORTS = {
     "wost_scene_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "wost_scene_destroy": (C.c_int, [C.c_void_p]),
     "wost_scene_trim": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "wost_selftest_division": (C.c_int, [C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "wost_field_create": (C.c_int, [C.POINTER(FieldDesc), C.c_int32, C.POINTER(C.c_void_p)]),
     "wost_field_destroy": (C.c_int, [C.c_void_p]),
     "wost_field_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

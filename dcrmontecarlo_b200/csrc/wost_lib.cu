@@ -78,6 +78,7 @@ struct wost_scene {
     float4* dwide_boxes = nullptr; WideBvh dwide{};                                   // same for the Dirichlet polyline (boxes only)
     float bvh_slack = 0.f;                             // ray/box slack (1e-4 of the scene scale)
     int neu_closed = 0;                                // first Neumann vertex == last
+    int dir_rcp = 0;                                   // Dirichlet table carries verified reciprocals of u.u (dirichlet_distance<RCP>)
     float phys_nudge = 0.f;                            // 1e-5 of the scene scale
     float4* dseg_as_neu = nullptr;                     // the Dirichlet polyline in the Neumann layout and vice versa, for the
     float4* nseg_as_dir = nullptr;                     //   primitive entry points (intersect on `which = 0`, distance on `which = 1`)
@@ -543,6 +544,89 @@ static walk_kernel_t pick_kernel(bool neu, bool src, bool delta, bool phys) {
 
 // the device copy of a smooth-circle term carries the squared radii beyond which the step is exactly 0 / 1 in its
 // (otherwise unused) w1x / w1y slots: same fp32 expressions as the oracle evaluates per call
+// Correctly rounded reciprocal y of b, and the proof by exhaustion that  q0 = a y; r = fma(-b, q0, a); q = fma(y, r, q0)
+// equals the IEEE quotient a / b for every numerator (all 2^23 mantissas of one binade: scaling by powers of two is exact).
+// Used for the divisions by the Dirichlet segments' u.u (dirichlet_distance<RCP>, wost_device.cuh).  ~30 ms per divisor.
+static bool verified_reciprocal(float b, float* y_out) {
+    static std::mutex mu;
+    static std::map<uint32_t, std::pair<bool, float>> memo;
+    uint32_t key; std::memcpy(&key, &b, 4);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(key);
+    if (it == memo.end()) {
+        bool ok = b >= 9.094947e-13f && b <= 1.0995116e12f;               // [2^-40, 2^40]: nothing under- or overflows on the way
+        float y = 0.0f;
+        if (ok) {
+            y = (float)(1.0 / (double)b);
+            double err = std::fabs(1.0 - (double)b * (double)y);           // b y is exact in double: pick the nearest of the neighbours
+            for (float c : {std::nextafterf(y, 0.0f), std::nextafterf(y, INFINITY)}) {
+                const double e = std::fabs(1.0 - (double)b * (double)c);
+                if (e < err) { err = e; y = c; }
+            }
+            for (uint32_t m = 0; m < (1u << 23) && ok; ++m) {
+                const uint32_t bits = 0x3f800000u | m;
+                float a; std::memcpy(&a, &bits, 4);
+                volatile float q0 = a * y;
+                const float r = std::fmaf(-b, q0, a);
+                const float q = std::fmaf(y, r, q0);
+                volatile float ref = a / b;
+                ok = q == ref;
+            }
+        }
+        it = memo.emplace(key, std::make_pair(ok, y)).first;
+    }
+    *y_out = it->second.second;
+    return it->second.first;
+}
+
+// Brute-force check of the two hand-written division sequences against the compiler's IEEE division (tests, -m gpu):
+// [0] div2_by_near_one on unit directions (cos t, sin t) / |(cos t, sin t)|, [1] the same on random a in [-2, 2], b in
+// [1/2, 2), [2] the reciprocal sequence of dirichlet_distance<RCP> on the given divisors with random in-range numerators.
+__global__ void division_selftest_kernel(long long n, uint32_t k0, uint32_t k1, const float* __restrict__ by, int n_div, unsigned long long* mism) {
+    unsigned long long bad0 = 0, bad1 = 0, bad2 = 0, bad3 = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, 7u, k0, k1, o);
+        {   // the walk's own use: a direction from the walk's sincos, normalised
+            const float theta = (u24(o[0]) * 2.0f) * 3.14159274101257324f * ((o[1] & 1u) ? 0.5f : 1.0f) + ((o[1] & 2u) ? u24(o[2]) * 6.5f - 3.2f : 0.0f);
+            float sn, cs; wm_sincosf_small(theta, &sn, &cs);
+            const float dn = sqrt_in_range(norm2_sq(cs, sn));
+            bad3 += __float_as_uint(dn) != __float_as_uint(norm2(cs, sn));
+            float q0, q1; div2_by_near_one(cs, sn, dn, q0, q1);
+            volatile float r0 = cs / dn, r1 = sn / dn;
+            bad0 += (__float_as_uint(q0) != __float_as_uint(r0)) + (__float_as_uint(q1) != __float_as_uint(r1));
+        }
+        {   // random operands over the whole admitted range
+            const float b = __uint_as_float(0x3f000000u | (o[3] & 0x00ffffffu));                       // [1/2, 2)
+            const uint32_t ea = 67u + (o[1] >> 8) % 62u;                                               // 2^-60 ... 2^1
+            const float a0 = __uint_as_float((o[0] & 0x80000000u) | (ea << 23) | (o[0] & 0x007fffffu));
+            const float a1 = (o[2] & 0xffu) == 0u ? 0.0f : __uint_as_float((o[2] & 0x80000000u) | (((67u + (o[2] >> 8) % 62u)) << 23) | (o[1] & 0x007fffffu));
+            float q0, q1; div2_by_near_one(a0, a1, b, q0, q1);
+            volatile float r0 = a0 / b, r1 = a1 / b;
+            bad1 += (__float_as_uint(q0) != __float_as_uint(r0)) + (__float_as_uint(q1 + 0.0f) != __float_as_uint(r1 + 0.0f));
+        }
+        {   // square roots over [2^-100, 2^127]
+            const float x = __uint_as_float(((27u + (o[3] >> 8) % 228u) << 23) | (o[0] & 0x007fffffu));
+            volatile float r = sqrtf(x);
+            bad3 += __float_as_uint(sqrt_in_range(x)) != __float_as_uint(r);
+        }
+        if (n_div > 0) {
+            const int k = (int)(o[3] >> 24) % n_div;
+            const float b = by[k], y = by[n_div + k];
+            const uint32_t ea = 67u + (o[2] >> 8) % 120u;                                              // 2^-60 ... 2^59
+            const float a = __uint_as_float((o[1] & 0x80000000u) | (ea << 23) | (o[2] & 0x007fffffu));
+            const float p = a * y;
+            const float q = fmaf(y, fmaf(-b, p, a), p);
+            volatile float r = a / b;
+            bad2 += __float_as_uint(q) != __float_as_uint(r);
+        }
+    }
+    if (bad0) atomicAdd(mism, bad0);
+    if (bad1) atomicAdd(mism + 1, bad1);
+    if (bad2) atomicAdd(mism + 2, bad2);
+    if (bad3) atomicAdd(mism + 3, bad3);
+}
+
 static std::vector<wost_term_t> device_form_terms(const wost_field_desc_t* d) {
     std::vector<wost_term_t> terms(d->terms, d->terms + (d->kind == WOST_FIELD_TERMS ? d->n_terms : 0));
     for (auto& t : terms)
@@ -606,6 +690,25 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         ns[2 * k] = make_float4(ax, ay, ux, uy);
         ns[2 * k + 1] = make_float4(nx, ny, atan2f(ny, nx), 0.0f);       // solvers/WoStSolver.py:228
     }
+    // reciprocals of u.u for the scene-specialised kernels' Dirichlet distance -- only if every segment's divisor verifies
+    // (polylines of at most 64 segments with at most 8 distinct lengths: squares, regular polygons, surface lines)
+    int dir_rcp = 0;
+    if (nd - 1 <= 64 && env_int("WOST_DIRICHLET_RCP", 1)) {
+        std::map<uint32_t, float> ys;
+        bool ok = true;
+        for (int k = 0; k + 1 < nd && ok; ++k) {
+            uint32_t key; std::memcpy(&key, &ds[2 * k + 1].z, 4);
+            if (!ys.count(key)) {
+                float y = 0.0f;
+                ok = ys.size() < 8 && verified_reciprocal(ds[2 * k + 1].z, &y);
+                ys[key] = y;
+            }
+        }
+        if (ok) {
+            for (int k = 0; k + 1 < nd; ++k) { uint32_t key; std::memcpy(&key, &ds[2 * k + 1].z, 4); ds[2 * k + 1].w = ys[key]; }
+            dir_rcp = 1;
+        }
+    }
     // the other layout of each polyline, for the primitive entry points (PolyLinesSimple methods work on either boundary)
     std::vector<float4> ds_n(ds.size()), ns_d(ns.size());
     for (int k = 0; k + 1 < nd; ++k) {
@@ -662,6 +765,7 @@ int wost_scene_create(const float* dxy, int32_t nd, const float* nxy, int32_t nn
         s->bvh_slack = (float)(1e-4 * scale + 1e-30);
         s->phys_nudge = (float)(1e-5 * scale);
         s->neu_closed = (nn >= 4 && nxy[0] == nxy[2 * nn - 2] && nxy[1] == nxy[2 * nn - 1]) ? 1 : 0;
+        s->dir_rcp = dir_rcp;
         cudaError_t be = cudaSuccess;
         if (s->n_dseg >= env_int("WOST_BVH_MIN_DIRICHLET", 48)) {
             const std::vector<float4> nodes = build_bvh(dxy, nd, inflate, &s->dbvh_leaves);
@@ -1068,6 +1172,7 @@ static int solve_impl(const wost_scene_t* scene, const wost_fields_t* fields, co
                 // small scene: its sizes and query strategy become compile-time constants too
                 fl.n_dseg = scene->n_dseg; fl.n_nseg = scene->n_nseg; fl.sil_coop_max = a.sil_coop_max; fl.ray_coop_max = a.ray_coop_max;
                 fl.stage = stage_smem;
+                fl.dir_rcp = scene->dir_rcp != 0;
             }
             wost_fields_t none{};
             K = jit::get(fields ? fields : &none, fl, scene->device, mode == 1 || (long long)n_pts * W >= (1ll << 18),
@@ -1310,7 +1415,8 @@ int wost_jit_offline(const wost_field_desc_t* const descs[5] /* g, f, alpha, sig
         *slots[i] = &tmp[i];
     }
     jit::Flags fl{neu != 0, src != 0, delta != 0, trace != 0, phys != 0, big != 0, multi != 0, sp_mode, min_blocks};
-    if (n_dseg >= 0) { fl.n_dseg = n_dseg; fl.n_nseg = n_nseg; coop_thresholds(n_nseg, &fl.sil_coop_max, &fl.ray_coop_max); fl.stage = 1 | (n_nseg ? 2 : 0); }
+    if (n_dseg >= 0) { fl.n_dseg = n_dseg; fl.n_nseg = n_nseg; coop_thresholds(n_nseg, &fl.sil_coop_max, &fl.ray_coop_max); fl.stage = 1 | (n_nseg ? 2 : 0);
+                       fl.dir_rcp = env_int("WOST_DIRICHLET_RCP", 1) != 0; }
     const std::string source = jit::generate(&F, fl);
     const std::string pre = prefix ? prefix : "wost_walk_jit";
     if (FILE* fp = std::fopen((pre + ".cu").c_str(), "w")) { std::fwrite(source.data(), 1, source.size(), fp); std::fclose(fp); }
@@ -1335,6 +1441,33 @@ const char* wost_jit_last_note(void) {
     std::lock_guard<std::mutex> lk(jit::g_mu);
     note = jit::g_last_note;
     return note.c_str();
+}
+
+int wost_selftest_division(int32_t device, int64_t n, uint64_t seed, const float* divisors, int32_t n_divisors, int64_t out_mismatches[4]) {
+    if (wost_device_count() <= 0) return fail(WOST_ERR_CUDA, "no CUDA device available");
+    if (n <= 0 || !out_mismatches || (n_divisors > 0 && !divisors) || n_divisors > 64) return fail(WOST_ERR_INVALID, "bad arguments");
+    DeviceGuard g(device);
+    float ys[64]; float bs[64];
+    for (int k = 0; k < n_divisors; ++k) {
+        bs[k] = divisors[k];
+        if (!verified_reciprocal(bs[k], &ys[k])) return fail(WOST_ERR_INVALID, "divisor " + std::to_string(k) + " does not verify (out of [2^-40, 2^40]?)");
+    }
+    unsigned long long* d = nullptr; float* dby = nullptr;
+    CU(cudaMalloc((void**)&d, 4 * sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+    if (n_divisors > 0) {
+        CU(cudaMalloc((void**)&dby, 2 * sizeof(float) * n_divisors));
+        CU(cudaMemcpy(dby, bs, sizeof(float) * n_divisors, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dby + n_divisors, ys, sizeof(float) * n_divisors, cudaMemcpyHostToDevice));
+    }
+    const int threads = 256; const long long blocks = std::min<long long>((n + threads - 1) / threads, 148 * 32);
+    division_selftest_kernel<<<(unsigned)blocks, threads>>>(n, (uint32_t)seed, (uint32_t)(seed >> 32), dby, n_divisors, d);
+    CU(cudaGetLastError());
+    unsigned long long h[4];
+    CU(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(dby);
+    for (int i = 0; i < 4; ++i) out_mismatches[i] = (int64_t)h[i];
+    return WOST_OK;
 }
 
 int wost_fp32_peak(int32_t device, double* out_tflops, double* out_sm_mhz_effective) {

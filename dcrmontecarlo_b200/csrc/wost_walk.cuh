@@ -108,6 +108,8 @@ struct InterpFP {
     static constexpr bool STAGE_FIELDS = true;         // copy field headers / terms to shared memory at CTA start
     static constexpr bool MULTI = true;                // shared-walk multi-source code compiled in
     static constexpr int N_DSEG = -1, N_NSEG = -1, SIL_COOP_MAX = 0, RAY_COOP_MAX = 0, STAGE = 0;   // scene sizes: run-time values (WalkArgs)
+    static constexpr bool DIR_RCP = false;             // Dirichlet distance: generic IEEE division (dirichlet_distance, wost_device.cuh)
+    static constexpr bool ALPHA_IN_RANGE = false;      // alpha's bounds are not known at compile time
     __device__ __forceinline__ static bool has_g(const WalkArgs& a) { return a.F.g.present != 0; }
     __device__ __forceinline__ static bool has_alpha(const WalkArgs& a) { return a.F.alpha.present != 0; }
     __device__ __forceinline__ static bool has_sigma(const WalkArgs& a) { return a.F.sigma.present != 0; }
@@ -303,7 +305,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
         // physical:  the distance at the current position decides, and g is read at the closest boundary point.
         int dir_arg = -1;
         if (PHYS && active)
-            dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, n_dseg, a.dbvh, x, y, &dir_arg) : dirichlet_distance(dseg, n_dseg, x, y, &dir_arg);
+            dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, n_dseg, a.dbvh, x, y, &dir_arg) : dirichlet_distance<FP::DIR_RCP>(dseg, n_dseg, x, y, &dir_arg);
         const bool stepping = active && steps < a.max_steps && dD > a.eps && !(PHYS && DELTA && atten == 0.0f);   // weight 0: absorbed
         {
             // terminal: the boundary contribution is read at the un-projected point (:295-298, Q5/Q7); park the walk.
@@ -349,7 +351,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
         if (stepping) {
             if (!PHYS && !(BIG && a.dwide.boxes))
                 dD = (BIG && a.dbvh.nodes) ? bvh_dirichlet_distance(a.dseg, n_dseg, a.dbvh, x, y, nullptr)
-                                  : dirichlet_distance(dseg, n_dseg, x, y, nullptr);      // :208
+                                  : dirichlet_distance<FP::DIR_RCP>(dseg, n_dseg, x, y, nullptr);      // :208
             uint32_t w0;
             if (PHYS) {
                 philox4x32_10_ks(pidx, widx, (uint32_t)steps, 2u, a.ks, o);      // stream tag 2: physical mode
@@ -377,8 +379,8 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 if (PHYS) { ex = dx; ey = dy; ox = x; oy = y; }
                 else {
                     // intersect_polylines_jit prologue (:149-159): normalise, offset the origin by 1e-6
-                    const float dn = norm2(dx, dy);
-                    ex = dx / dn; ey = dy / dn;
+                    const float dn = sqrt_in_range(norm2_sq(dx, dy));                   // torch.norm (:151); 1 to within a few ulp: (dx, dy) = (cos, sin)
+                    div2_by_near_one(dx, dy, dn, ex, ey);                               // ex = dx / dn, ey = dy / dn (:152)
                     ox = x + 1e-6f * ex; oy = y + 1e-6f * ey;
                 }
                 // the silhouette distance only matters if it can be smaller than dDirichlet (:212): every Neumann
@@ -653,7 +655,7 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                         });
                     } else if (DELTA) {                                                 // :252-254
                         if (!have_alpha_s) { alpha_s = FP::alpha(a, sx, sy); have_alpha_s = true; }
-                        contrib = div_z(FP::f(a, sx, sy) * gn, sqrtf(alpha_s * alpha_x)) * atten;
+                        contrib = div_z(FP::f(a, sx, sy) * gn, FP::ALPHA_IN_RANGE ? sqrt_in_range(alpha_s * alpha_x) : sqrtf(alpha_s * alpha_x)) * atten;
                     } else
                         contrib = FP::f(a, sx, sy) * (r * r / 4.0f);       // :256
                 }
@@ -669,7 +671,9 @@ __device__ __forceinline__ void walk_body(const WalkArgs& a) {
                 // branch at next_point, the interior branch at sample_point unless the source term already did).
                 const float tx = edge ? qx : sx, ty = edge ? qy : sy;
                 const float alpha_t = have_jet_s ? jet_s.v : ((!edge && have_alpha_s) ? alpha_s : FP::alpha(a, tx, ty));
-                const float ratio = sqrtf(alpha_t / alpha_x);
+                // specialised kernels whose alpha is bounded away from 0 and infinity (2^-30 ... 2^30, known when the kernel is
+                // generated): quotient and root by the compiler's own fast-path sequences without their range checks
+                const float ratio = FP::ALPHA_IN_RANGE ? sqrt_in_range(div_in_range(alpha_t, alpha_x)) : sqrtf(alpha_t / alpha_x);
                 if (edge) {
                     atten = atten * ratio;                                              // :277
                 } else {

@@ -229,6 +229,13 @@ int wost_jit_offline(const wost_field_desc_t* const descs[5], int32_t neu, int32
                      int32_t phys, int32_t big, int32_t multi, int32_t sp_mode, int32_t min_blocks,
                      int32_t n_dirichlet_seg /* -1: run-time sizes */, int32_t n_neumann_seg, const char* arch, const char* prefix);
 
+/* Self-test (tests): n random operand sets through the library's two hand-written division sequences (csrc/wost_device.cuh:
+ * div2_by_near_one; the reciprocal form of dirichlet_distance<RCP> for the given divisors, each verified on the host first)
+ * and square root (sqrt_in_range) against the compiler's IEEE operations.  out_mismatches = {quotients of unit directions,
+ * random operands near one, reciprocal form, square roots}. */
+int wost_selftest_division(int32_t device, int64_t n, uint64_t seed, const float* divisors, int32_t n_divisors,
+                           int64_t out_mismatches[4]);
+
 /* FP32 FMA-chain microbenchmark: measured non-tensor fp32 TFLOP/s of the device (roofline denominator) */
 int wost_fp32_peak(int32_t device, double* out_tflops, double* out_sm_mhz_effective);
 #endif /* __CUDACC_RTC__ */

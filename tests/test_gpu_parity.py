@@ -891,3 +891,17 @@ def test_jit_random_fields_equal_static_and_oracle():
         prob = orc.Problem(s.dirichlet, s.neumann, g=g, f=f, alpha=alpha, sigma=sigma, sigma_bar=solver.sigma_bar, sp_mode=solver.sp_mode)
         o = prob.solve(pts, 300, 300, 1e-3, rng_mode=orc.RNG_PHILOX, seed=trial, icdf=icdf, walk_vals=True)
         assert np.array_equal(bits(a["walk_vals"]), bits(o["walk_vals"])), trial
+
+
+def test_hand_written_division_sequences_equal_ieee_division():
+    """div2_by_near_one (direction normalisation), the reciprocal form of the Dirichlet distance's division
+    (dirichlet_distance<RCP>, divisors verified exhaustively on the host) and sqrt_in_range against the compiler's IEEE
+    division / square root on 2^28 random operand sets each: not one differing bit."""
+    import ctypes as C
+
+    divs = np.array([40000.0, 4.0, 16.0, 9.0, 0.59969723, 1e-3, 12345.678, 1.0000001, 1.9999999], np.float32)
+    out = (C.c_int64 * 4)()
+    nat.check(nat.lib().wost_selftest_division(nat.current_device(), 1 << 28, 20261018, divs.ctypes.data_as(C.c_void_p), len(divs), out))
+    assert list(out) == [0, 0, 0, 0], list(out)
+    bad = np.array([1e-20], np.float32)                      # outside [2^-40, 2^40]: refused, the scene would keep the generic division
+    assert nat.lib().wost_selftest_division(nat.current_device(), 16, 1, bad.ctypes.data_as(C.c_void_p), 1, out) != 0
