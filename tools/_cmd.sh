@@ -1,5 +1,3 @@
 set -x
-( time timeout 600 python -m pytest tests/test_gpu_multi.py -x -q ) > gpurun_out/r2_pytest_multi.log 2>&1; tail -n 4 gpurun_out/r2_pytest_multi.log
-for N in 8 2; do
-  ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 ) > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo rc=$?; tail -c 300 gpurun_out/r2_bench_n$N.err
-done
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2o_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2o_pytest_gpu.log
+bash tools/ab.sh "build/libwost_v16.so build/libwost_v17.so" cfg5 cfg1b > gpurun_out/r2o_ab.txt 2>&1
