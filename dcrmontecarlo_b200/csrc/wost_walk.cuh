@@ -143,18 +143,9 @@ __device__ __forceinline__ float sigma_prime_fp(const WalkArgs& a, float x, floa
     Jet j; j.v = 1.0f; j.gx = j.gy = j.l = 0.0f;
     if (FP::has_alpha(a)) j = jet ? *jet : FP::alpha_jet(a, x, y);
     if (j.v < 1e-8f) { j.v = 1e-8f; j.gx = j.gy = j.l = 0.0f; }
-    const float la = j.v + 1e-8f, lap = j.l + 1e-8f;
-    if (FP::ALPHA_IN_RANGE && in_quotient_range(sg) && in_quotient_range(j.gx) && in_quotient_range(j.gy) && in_quotient_range(lap)) {
-        // alpha is bounded (known when this kernel was generated), so the four quotients -- two divisors -- run the
-        // compiler's fast-path sequence on two shared reciprocals without range checks; the numerators are exactly zero away
-        // from alpha's rims (0 / b = 0 through the sequence) and only a numerator below 2^-60 takes the generic divisions
-        const float yv = refined_rcp(j.v), ya = refined_rcp(la);
-        const float lgx = quotient_by(j.gx, la, ya), lgy = quotient_by(j.gy, la, ya);
-        return quotient_by(sg, j.v, yv) + 0.5f * (quotient_by(lap, j.v, yv) - (lgx * lgx + lgy * lgy) / 2.0f);
-    }
     const float ratio = div_z(sg, j.v);
-    const float lgx = div_z(j.gx, la), lgy = div_z(j.gy, la);
-    const float corr = 0.5f * (lap / j.v - (lgx * lgx + lgy * lgy) / 2.0f);
+    const float la = j.v + 1e-8f, lgx = div_z(j.gx, la), lgy = div_z(j.gy, la);
+    const float corr = 0.5f * ((j.l + 1e-8f) / j.v - (lgx * lgx + lgy * lgy) / 2.0f);
     return ratio + corr;
 }
 
