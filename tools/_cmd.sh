@@ -1,3 +1,4 @@
-set -x
-( time timeout 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2t_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2t_pytest_gpu.log
-for s in cfg2 cfg4; do python tools/run_one.py $s 5 | tail -1; done > gpurun_out/r2t_run.txt 2>&1
+( time timeout 600 python bench.py ) > gpurun_out/r2u_bench1.json 2> gpurun_out/r2u_bench1.err
+for s in cfg2 cfg4; do
+  timeout 300 ncu --set full --clock-control none -k regex:walk --launch-skip 2 -c 1 -f -o gpurun_out/r2u_full_$s python tools/run_one.py $s 4 > gpurun_out/r2u_ncu_full_$s.log 2>&1
+done
