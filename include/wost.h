@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WOST_VERSION 200   /* major*10000 + minor*100 + patch */
+#define WOST_VERSION 201   /* major*10000 + minor*100 + patch */
 
 typedef enum {
     WOST_OK = 0,

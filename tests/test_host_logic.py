@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = nat.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.wost_version() == 200
+    assert L.wost_version() == 201
     assert L.wost_device_count() >= 0
 
 
