@@ -124,3 +124,15 @@ class PolyLinesSimple(PolyLines):
         if single:
             return tp[0], tn[0], bool(found[0])
         return tp, tn, torch.from_numpy(found.astype(bool)).to(dev)
+
+
+class PolyLinesBVH(PolyLinesSimple):
+    """The spatially accelerated polyline the reference's abstract base was written for (``geometry/Polylines.py:8-63``;
+    SURVEY §8 f-3), under the name a user of the reference would look for.  Every polyline gets its hierarchy automatically
+    once it is large enough (implicit tree over the index order with silhouette normal cones, built in ``wost_scene_create``:
+    >= 48 Dirichlet / >= 192 Neumann segments, 32-wide cooperative trees from 512 segments) and answers every query with the
+    bits of the brute-force loops, so this class adds nothing but ``has_hierarchy``."""
+
+    @property
+    def has_hierarchy(self) -> bool:
+        return len(self.points) - 1 >= 48

@@ -1,7 +1,7 @@
 """Polyline boundaries for Walk on Stars: the abstract interface and the GPU brute-force / BVH implementation."""
 import importlib
 
-_EXPORTS = {"PolyLines": "Polylines", "PolyLinesSimple": "PolylinesSimple", "PolyLinesBVH": "PolylinesBVH"}
+_EXPORTS = {"PolyLines": "Polylines", "PolyLinesSimple": "PolylinesSimple", "PolyLinesBVH": "PolylinesSimple"}
 __all__ = sorted(_EXPORTS)
 
 
