@@ -1,4 +1,3 @@
-( time timeout 600 python bench.py ) > gpurun_out/r2u_bench1.json 2> gpurun_out/r2u_bench1.err
-for s in cfg2 cfg4; do
-  timeout 300 ncu --set full --clock-control none -k regex:walk --launch-skip 2 -c 1 -f -o gpurun_out/r2u_full_$s python tools/run_one.py $s 4 > gpurun_out/r2u_ncu_full_$s.log 2>&1
-done
+( time timeout 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2v_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/r2v_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2v_smoke.txt 2>&1; tail -2 gpurun_out/r2v_smoke.txt
+python bench.py --headline-only --steps 5 --warmup 3 > gpurun_out/r2v_headline.json 2>/dev/null; cat gpurun_out/r2v_headline.json | cut -c1-200
