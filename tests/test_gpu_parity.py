@@ -196,6 +196,13 @@ def test_estimates_within_3_sigma_of_reference(golden, key):
     z = (r["mean"] - ref_mean) / np.sqrt(se_gpu ** 2 + se_ref ** 2 + 1e-30)
     assert np.mean(np.abs(z) <= 3.0) >= 0.95, z
     assert abs(np.mean(z)) < 4.0 / np.sqrt(len(z)) + 0.35
+    if key != "cfg5":
+        # the same bar with an INDEPENDENT error bar: the reference's own sample variance over its n_ref walks.  (Not for
+        # cfg 5: with 150 heavy-tailed walks per electrode the reference's sample variance misses the rare large
+        # contributions -- it underestimates the standard error severalfold and is zero at 4 of the 9 electrodes.)
+        se_own = W["walk_vals"].std(axis=1, ddof=1) / np.sqrt(n_ref)
+        z_own = (r["mean"] - ref_mean) / np.sqrt(se_gpu ** 2 + se_own ** 2 + 1e-30)
+        assert np.mean(np.abs(z_own) <= 3.0) >= 0.95, z_own
     assert abs(int(r["steps"][0]) / (nw * len(W["points"])) / W["walk_steps"].mean() - 1.0) < 0.08
 
 
